@@ -1,0 +1,52 @@
+"""ctypes binding of libflair_b200.so (the C ABI declared in include/flair_b200.h).
+
+The library is built in-tree by `flair_b200.build`; there is deliberately no
+fallback: if the shared object is missing the import of any op fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libflair_b200.so"
+
+BF16, F32, F16 = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LRELU01, ACT_SILU = 0, 1, 2, 3
+OUT_NHWC, OUT_NCHW = 0, 1
+
+
+class ConvParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("B", C.c_int), ("T", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("Cin", C.c_int), ("x_cstride", C.c_int), ("wgt", C.c_void_p), ("Cout", C.c_int),
+        ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("stride_hw", C.c_int),
+        ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_stride", C.c_int),
+        ("residual", C.c_void_p), ("residual_dtype", C.c_int), ("residual_cstride", C.c_int),
+        ("out", C.c_void_p), ("out_dtype", C.c_int), ("out_layout", C.c_int),
+        ("out_cstride", C.c_int), ("act", C.c_int), ("in_dtype", C.c_int),
+        ("out_scale", C.c_float), ("gn_partial", C.c_void_p), ("gn_groups", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: run `python -m flair_b200.build` (nvcc, sm_100a). "
+                "flair_b200 has no CPU or PyTorch fallback."
+            )
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.flair_last_error.restype = C.c_char_p
+        _lib.flair_version.restype = C.c_int
+        _lib.flair_check_device.argtypes = [C.c_int]
+        _lib.flair_conv_igemm.argtypes = [C.POINTER(ConvParams), C.c_void_p]
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"flair_b200: {lib().flair_last_error().decode()} (rc={rc})")

@@ -1,0 +1,68 @@
+// Library-wide plumbing of the C ABI: error string, device check, driver entry
+// points.  See include/flair_b200.h for the conventions.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "../../include/flair_b200.h"
+
+namespace {
+thread_local char g_err[1024] = "";
+}
+
+void flair_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int flair_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+flair_tmap_encode_fn flair_get_tmap_encode() {
+  static flair_tmap_encode_fn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<flair_tmap_encode_fn>(sym);
+    }
+  }
+  return fn;
+}
+
+extern "C" const char* flair_last_error(void) { return g_err; }
+extern "C" int flair_version(void) { return FLAIR_B200_VERSION; }
+
+extern "C" int flair_check_device(int dev) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    flair_set_error("flair_check_device: no CUDA device visible (this library has no CPU path)");
+    return FLAIR_ERR_UNSUPPORTED;
+  }
+  if (dev < 0 || dev >= count) {
+    flair_set_error("flair_check_device: device %d out of range (0..%d)", dev, count - 1);
+    return FLAIR_ERR_INVALID;
+  }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) {
+    flair_set_error("flair_check_device: device %d is sm_%d%d; kernels are built for sm_100a only",
+                    dev, major, minor);
+    return FLAIR_ERR_UNSUPPORTED;
+  }
+  return 0;
+}

@@ -1,0 +1,482 @@
+// Implicit-GEMM convolution / GEMM for sm_100a: TMA -> 128B-swizzled smem ->
+// tcgen05.mma (UMMA, M=128) -> fp32 accumulators in TMEM -> fused epilogue.
+//
+// Replaces (reference, paths relative to the FLAIR checkout): every nn.Conv2d /
+// nn.Conv3d / nn.Conv1d(k=1) / nn.Linear of the UNet torso, e.g.
+// guided_diffusion/unet_new.py:240-244 (ResBlock in conv), :271-276 (out conv),
+// :292-295 (1x1 skip), :359,367 (qkv / proj), :455-457 (temporal q/k/v),
+// :859-867 (BasicVSR++ offset net); guided_diffusion/sr3.py:95-120.
+//
+// Data layout.  Activations are channels-last [B][T][H][W][C] (16-bit), so an
+// output tile of 128 pixels x 64 input channels is exactly one TMA box
+// {64, bw, bh, bt, 1}; it lands in smem as 128 rows of 128 B, i.e. the canonical
+// K-major SWIZZLE_128B UMMA operand.  A filter tap (dt,dh,dw) is nothing but a
+// shifted box origin, and TMA's out-of-bounds zero fill *is* the zero padding.
+// Weights are packed [tap][Cout_pad][Cin_pad] so a (n_tile x 64) slab of one tap
+// is one 2-D box, also K-major.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+// alloc), warps 2..5 = epilogue (one TMEM lane quarter each).  The kernel is
+// persistent: grid = min(#tiles, #SMs); accumulators are double-buffered in
+// TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "../../include/flair_b200.h"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 x 16-bit = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kMaxTaps = 27;
+constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
+
+struct ConvKArgs {
+  int B, T, Ho, Wo;
+  int lbw, lbh, lbt;  // log2 of the tile box extents (bw*bh*bt == 128)
+  int tiles_w, tiles_h, tiles_t;
+  int m_tiles, n_tiles;
+  int n_tile;   // accumulator columns per tile (multiple of 16, <= 256)
+  int acc_cols; // TMEM column offset between the two accumulator buffers
+  int tmem_cols;
+  int Cout, Cout_pad;
+  int kblocks, ntaps, stride;
+  int stages;
+  int8_t tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dt[kMaxTaps];
+  const float* bias;
+  const float* rowbias;
+  int rowbias_stride;
+  const void* residual;
+  int residual_dtype;
+  long long residual_cstride;
+  void* out;
+  int out_dtype, out_layout;
+  long long out_cstride;
+  int act;
+  float out_scale;
+  uint32_t fmt;
+  float* gn_partial;
+  int gn_groups;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case FLAIR_ACT_RELU: return fmaxf(v, 0.0f);
+    case FLAIR_ACT_LRELU01: return v > 0.0f ? v : 0.1f * v;
+    case FLAIR_ACT_SILU: return silu_f(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, int dtype) {
+  if (dtype == FLAIR_F16) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t u, int dtype) {
+  if (dtype == FLAIR_F16) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
+  }
+  return unpack_bf16x2(u);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ ConvKArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A 16 KB][B n_tile*128 B] then barriers
+  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * kBlockK * 2;
+  const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(a.stages) * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + a.stages;
+  uint64_t* tfull_bar = bars + 2 * a.stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(a.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = a.m_tiles * a.n_tiles;
+  const int k_iters = a.ntaps * a.kblocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_idx = tile % a.n_tiles;
+        int m_idx = tile / a.n_tiles;
+        const int tw = m_idx % a.tiles_w; m_idx /= a.tiles_w;
+        const int th = m_idx % a.tiles_h; m_idx /= a.tiles_h;
+        const int tt = m_idx % a.tiles_t;
+        const int b = m_idx / a.tiles_t;
+        const int w0 = (tw << a.lbw) * a.stride;
+        const int h0 = (th << a.lbh) * a.stride;
+        const int t0 = tt << a.lbt;
+        for (int tap = 0; tap < a.ntaps; ++tap) {
+          const int cw = w0 + a.tap_dw[tap];
+          const int ch = h0 + a.tap_dh[tap];
+          const int ct = t0 + a.tap_dt[tap];
+          const int brow = tap * a.Cout_pad + n_idx * a.n_tile;
+          for (int kb = 0; kb < a.kblocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_expect_tx(&full_bar[stage], kABytes + b_bytes);
+            tma_load_5d(sa, &tmA, &full_bar[stage], kb * kBlockK, cw, ch, ct, b);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, brow);
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_f16(kBlockM, static_cast<uint32_t>(a.n_tile), a.fmt);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * a.acc_cols);
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // +32 B per K step inside the 128 B swizzle row (encoded >> 4)
+            umma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                     idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;
+    const int bw = 1 << a.lbw, bh = 1 << a.lbh;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int n_idx = tile % a.n_tiles;
+      int m_idx = tile / a.n_tiles;
+      const int tw = m_idx % a.tiles_w; m_idx /= a.tiles_w;
+      const int th = m_idx % a.tiles_h; m_idx /= a.tiles_h;
+      const int tt = m_idx % a.tiles_t;
+      const int b = m_idx / a.tiles_t;
+      const int w = (tw << a.lbw) + (row & (bw - 1));
+      const int h = (th << a.lbh) + ((row >> a.lbw) & (bh - 1));
+      const int t = (tt << a.lbt) + (row >> (a.lbw + a.lbh));
+      const bool valid = (w < a.Wo) && (h < a.Ho) && (t < a.T);
+      const long long frame = static_cast<long long>(b) * a.T + t;
+      const long long pix = (frame * a.Ho + h) * a.Wo + w;
+      const int n0 = n_idx * a.n_tile;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * a.acc_cols) +
+                              (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+        uint32_t r[16];
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after divergent stores
+        tmem_ld16(t_addr + static_cast<uint32_t>(c0), r);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        if (n >= a.Cout) continue;  // warp-uniform: padded columns
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (a.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n + j < a.Cout) v[j] += __ldg(a.bias + n + j);
+        }
+        if (a.rowbias != nullptr && valid) {
+          const float* rb = a.rowbias + frame * a.rowbias_stride + n;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n + j < a.Cout) v[j] += __ldg(rb + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], a.act) * a.out_scale;
+
+        const bool full16 = (n + 16 <= a.Cout);
+        if (a.residual != nullptr && valid) {
+          if (a.residual_dtype == FLAIR_F32) {
+            const float* rp = static_cast<const float*>(a.residual) + pix * a.residual_cstride + n;
+            if (full16) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(rp) + q);
+                v[4 * q + 0] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
+              }
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (n + j < a.Cout) v[j] += __ldg(rp + j);
+            }
+          } else {
+            const uint16_t* rp =
+                static_cast<const uint16_t*>(a.residual) + pix * a.residual_cstride + n;
+            if (full16) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack16(uu[e], a.residual_dtype);
+                  v[8 * q + 2 * e] += f.x;
+                  v[8 * q + 2 * e + 1] += f.y;
+                }
+              }
+            } else {
+              for (int j = 0; j < 16; ++j) {
+                if (n + j < a.Cout) {
+                  const uint32_t u = rp[j];
+                  v[j] += unpack16(u, a.residual_dtype).x;
+                }
+              }
+            }
+          }
+        }
+        if (!valid) continue;
+        if (a.out_layout == FLAIR_OUT_NCHW) {
+          // fp32 planar output: (frame, n, h, w); lanes walk w -> coalesced per channel
+          float* op = static_cast<float*>(a.out);
+          const long long plane = static_cast<long long>(a.Ho) * a.Wo;
+          for (int j = 0; j < 16; ++j) {
+            if (n + j < a.Cout)
+              op[(frame * a.Cout + n + j) * plane + static_cast<long long>(h) * a.Wo + w] = v[j];
+          }
+        } else if (a.out_dtype == FLAIR_F32) {
+          float* op = static_cast<float*>(a.out) + pix * a.out_cstride + n;
+          if (full16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              reinterpret_cast<float4*>(op)[q] =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (n + j < a.Cout) op[j] = v[j];
+          }
+        } else {
+          uint16_t* op = static_cast<uint16_t*>(a.out) + pix * a.out_cstride + n;
+          if (full16) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              uint4 u;
+              u.x = pack16(v[8 * q + 0], v[8 * q + 1], a.out_dtype);
+              u.y = pack16(v[8 * q + 2], v[8 * q + 3], a.out_dtype);
+              u.z = pack16(v[8 * q + 4], v[8 * q + 5], a.out_dtype);
+              u.w = pack16(v[8 * q + 6], v[8 * q + 7], a.out_dtype);
+              reinterpret_cast<uint4*>(op)[q] = u;
+            }
+          } else {
+            for (int j = 0; j < 16; ++j) {
+              if (n + j < a.Cout) {
+                const uint32_t u = pack16(v[j], 0.0f, a.out_dtype);
+                op[j] = static_cast<uint16_t>(u & 0xFFFFu);
+              }
+            }
+          }
+        }
+      }
+      // this warp is done reading the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(a.tmem_cols));
+  }
+}
+
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << (l + 1)) <= v) ++l;
+  return l;
+}
+int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(p != nullptr, "flair_conv_igemm: null params");
+  FLAIR_REQUIRE(p->x && p->wgt && p->out, "flair_conv_igemm: null tensor pointer");
+  FLAIR_REQUIRE(p->B > 0 && p->T > 0 && p->H > 0 && p->W > 0 && p->Cin > 0 && p->Cout > 0,
+                "flair_conv_igemm: bad extents B=%d T=%d H=%d W=%d Cin=%d Cout=%d", p->B, p->T,
+                p->H, p->W, p->Cin, p->Cout);
+  FLAIR_REQUIRE((p->kt == 1 || p->kt == 3) && (p->kh == 1 || p->kh == 3) &&
+                    (p->kw == 1 || p->kw == 3),
+                "flair_conv_igemm: kernel extents must be 1 or 3 (got %d,%d,%d)", p->kt, p->kh,
+                p->kw);
+  FLAIR_REQUIRE(p->stride_hw == 1 || p->stride_hw == 2, "flair_conv_igemm: stride must be 1 or 2");
+  FLAIR_REQUIRE(p->x_cstride % 8 == 0 && p->x_cstride >= p->Cin,
+                "flair_conv_igemm: x_cstride=%d must be a multiple of 8 and >= Cin=%d",
+                p->x_cstride, p->Cin);
+  FLAIR_REQUIRE((reinterpret_cast<uintptr_t>(p->x) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(p->wgt) & 15) == 0,
+                "flair_conv_igemm: x / wgt must be 16-byte aligned");
+  FLAIR_REQUIRE(p->in_dtype == FLAIR_BF16 || p->in_dtype == FLAIR_F16,
+                "flair_conv_igemm: operands must be bf16 or fp16");
+  if (p->out_layout == FLAIR_OUT_NCHW)
+    FLAIR_REQUIRE(p->out_dtype == FLAIR_F32, "flair_conv_igemm: NCHW output is fp32 only");
+  else
+    FLAIR_REQUIRE(p->out_cstride >= p->Cout, "flair_conv_igemm: out_cstride < Cout");
+  FLAIR_REQUIRE(p->gn_partial == nullptr, "flair_conv_igemm: fused GN partials not enabled yet");
+
+  const int s = p->stride_hw;
+  const int Ho = (p->H + s - 1) / s, Wo = (p->W + s - 1) / s;
+  const int Cin_pad = ceil_div(p->Cin, kBlockK) * kBlockK;
+  const int Cout_pad = ceil_div(p->Cout, 16) * 16;
+
+  ConvKArgs a{};
+  a.B = p->B; a.T = p->T; a.Ho = Ho; a.Wo = Wo;
+  // tile box: as wide as possible, then tall, then across frames
+  int bw = pow2_ceil(Wo); if (bw > kBlockM) bw = kBlockM;
+  int bh = pow2_ceil(Ho); if (bh > kBlockM / bw) bh = kBlockM / bw;
+  int bt = kBlockM / (bw * bh);
+  a.lbw = ilog2(bw); a.lbh = ilog2(bh); a.lbt = ilog2(bt);
+  a.tiles_w = ceil_div(Wo, bw); a.tiles_h = ceil_div(Ho, bh); a.tiles_t = ceil_div(p->T, bt);
+  a.m_tiles = a.tiles_w * a.tiles_h * a.tiles_t * p->B;
+  int n_tile = Cout_pad;
+  if (n_tile > 256) {
+    n_tile = 256;
+    while (Cout_pad % n_tile != 0) n_tile -= 16;
+  }
+  a.n_tile = n_tile;
+  a.n_tiles = Cout_pad / n_tile;
+  a.tmem_cols = pow2_ceil(2 * n_tile < 32 ? 32 : 2 * n_tile);
+  a.acc_cols = a.tmem_cols / 2;
+  a.Cout = p->Cout; a.Cout_pad = Cout_pad;
+  a.kblocks = Cin_pad / kBlockK;
+  a.stride = s;
+  int nt = 0;
+  for (int dt = -(p->kt / 2); dt <= p->kt / 2; ++dt)
+    for (int dh = -(p->kh / 2); dh <= p->kh / 2; ++dh)
+      for (int dw = -(p->kw / 2); dw <= p->kw / 2; ++dw) {
+        a.tap_dt[nt] = static_cast<int8_t>(dt);
+        a.tap_dh[nt] = static_cast<int8_t>(dh);
+        a.tap_dw[nt] = static_cast<int8_t>(dw);
+        ++nt;
+      }
+  a.ntaps = nt;
+  a.bias = p->bias; a.rowbias = p->rowbias; a.rowbias_stride = p->rowbias_stride;
+  a.residual = p->residual; a.residual_dtype = p->residual_dtype;
+  a.residual_cstride = p->residual_cstride;
+  a.out = p->out; a.out_dtype = p->out_dtype; a.out_layout = p->out_layout;
+  a.out_cstride = p->out_cstride; a.act = p->act;
+  a.out_scale = (p->out_scale == 0.0f) ? 1.0f : p->out_scale;
+  a.fmt = (p->in_dtype == FLAIR_BF16) ? 1u : 0u;
+  a.gn_partial = nullptr; a.gn_groups = 0;
+
+  const uint32_t b_bytes = static_cast<uint32_t>(n_tile) * kBlockK * 2;
+  const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
+  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  int stages = smem_budget / static_cast<int>(stage_bytes);
+  if (stages > 8) stages = 8;
+  FLAIR_REQUIRE(stages >= 2, "flair_conv_igemm: tile does not fit shared memory");
+  a.stages = stages;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+
+  flair_tmap_encode_fn encode = flair_get_tmap_encode();
+  FLAIR_REQUIRE(encode != nullptr, "flair_conv_igemm: cuTensorMapEncodeTiled unavailable");
+  const CUtensorMapDataType dt16 =
+      (p->in_dtype == FLAIR_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(p->Cin), static_cast<cuuint64_t>(p->W),
+                          static_cast<cuuint64_t>(p->H), static_cast<cuuint64_t>(p->T),
+                          static_cast<cuuint64_t>(p->B)};
+    const cuuint64_t px = static_cast<cuuint64_t>(p->x_cstride) * 2;
+    cuuint64_t strides[4] = {px, px * p->W, px * p->W * p->H, px * p->W * p->H * p->T};
+    cuuint32_t box[5] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(bw * s),
+                         static_cast<cuuint32_t>(bh * s), static_cast<cuuint32_t>(bt), 1u};
+    if (s == 2) { box[1] -= 1; box[2] -= 1; }  // ceil(box/stride) == bw, no overreach
+    cuuint32_t estr[5] = {1u, static_cast<cuuint32_t>(s), static_cast<cuuint32_t>(s), 1u, 1u};
+    CUresult r = encode(&tmA, dt16, 5, const_cast<void*>(p->x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FLAIR_REQUIRE(r == CUDA_SUCCESS, "flair_conv_igemm: activation tensor map rejected (%d)",
+                  static_cast<int>(r));
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(Cin_pad),
+                          static_cast<cuuint64_t>(nt) * static_cast<cuuint64_t>(Cout_pad)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(Cin_pad) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(n_tile)};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = encode(&tmB, dt16, 2, const_cast<void*>(p->wgt), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FLAIR_REQUIRE(r == CUDA_SUCCESS, "flair_conv_igemm: weight tensor map rejected (%d)",
+                  static_cast<int>(r));
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    FLAIR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int total_tiles = a.m_tiles * a.n_tiles;
+  int grid = flair_num_sms();
+  if (grid > total_tiles) grid = total_tiles;
+  conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, a);
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}
