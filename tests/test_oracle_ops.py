@@ -1,0 +1,126 @@
+"""Pin the CPU oracle (oracle/) against vectors dumped from the reference itself
+(tests/golden, made by tools/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import degrade, sampler
+from oracle.schedule import Tables
+
+
+@pytest.mark.parametrize("task,name,n", [("gaussian", "face_blur", 1000), ("bicubic", "face_bicubic", 2000)])
+def test_schedule_tables(golden, task, name, n):
+    ref = golden("schedule.pt")[task]
+    tab = Tables(name, n, 100)
+    assert tab.timestep_map == ref["timestep_map"].tolist()
+    for k in ("betas", "alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_alphas_cumprod_prev",
+              "sqrt_one_minus_alphas_cumprod_prev", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod"):
+        np.testing.assert_array_equal(getattr(tab, k), ref[k].numpy(), err_msg=k)
+
+
+def test_timestep_maps_match_survey():
+    assert Tables("face_blur", 1000).timestep_map[:3] == [0, 10, 20]
+    assert Tables("face_blur", 1000).timestep_map[-3:] == [979, 989, 999]
+    assert Tables("face_bicubic", 2000).timestep_map[:4] == [0, 20, 40, 61]
+
+
+def _taps(golden):
+    t = golden("pseudosr_taps.pt")
+    return t["ds_kernel"].float(), t["inv_hTh"].float()
+
+
+def test_blur_operator_pieces(golden):
+    fx = golden("dc_gaussian.pt")
+    ds, inv = _taps(golden)
+    assert rel_err(degrade.blur_down(fx["x"], ds), fx["down_x"]) < 1e-6
+    assert rel_err(degrade.inv_hth(fx["y"], inv), fx["inv_y"]) < 1e-6
+    assert rel_err(degrade.up_blur(degrade.inv_hth(fx["y"], inv), ds), fx["up_inv_y"]) < 1e-6
+
+
+def test_blur_restore(golden):
+    fx = golden("dc_gaussian.pt")
+    ds, inv = _taps(golden)
+    assert rel_err(degrade.blur_restore(fx["x"], fx["y"], ds, inv), fx["R"]) < 1e-5
+
+
+def test_filter_weights_are_the_taps(golden):
+    t = golden("pseudosr_taps.pt")
+    ds, inv = _taps(golden)
+    assert torch.equal(t["w_down"], torch.flip(ds, (0, 1)))
+    assert torch.equal(t["w_inv"], inv)
+    assert torch.equal(t["w_up"], (t["ds_kernel"] * 16).float())
+    assert t["pre_stride"].tolist() == [1, 1] and t["post_stride"].tolist() == [2, 2]
+
+
+def test_jpeg_tables_and_dct(golden):
+    fx = golden("dc_jpeg.pt")
+    q1, q2 = degrade.quant_tables(fx["qf"])
+    assert torch.equal(q1, fx["q_luma"]) and torch.equal(q2, fx["q_chroma"])
+    assert torch.equal(degrade.dct8_matrix(), fx["dct"])
+    assert torch.equal(degrade.idct8_matrix(), fx["idct"])
+
+
+def test_jpeg_codec(golden):
+    fx = golden("dc_jpeg.pt")
+    enc = degrade.jpeg_encode(fx["img"], fx["qf"])
+    # quantised coefficients are integers: allow no more than a handful of round() ties to flip
+    assert (enc[0] != fx["enc_luma"]).sum() <= 2 and (enc[1] != fx["enc_chroma"]).sum() <= 2
+    dec = degrade.jpeg_decode([fx["enc_luma"], fx["enc_chroma"]], fx["qf"])
+    assert rel_err(dec, fx["dec"]) < 1e-6
+
+
+def test_jpeg_restore(golden):
+    fx = golden("dc_jpeg.pt")
+    ds, inv = _taps(golden)
+    R = degrade.blur_restore(fx["x"], fx["y"], ds, inv, jpeg_qf=fx["qf"])
+    assert rel_err(R, fx["R"]) < 1e-4  # a flipped round() moves one 8x8 block by one quant step
+
+
+@pytest.mark.parametrize("factor", [8, 16])
+def test_srconv(golden, factor):
+    fx = golden(f"dc_srconv_x{factor}.pt")
+    assert torch.equal(degrade.bicubic_taps(factor), fx["taps"])
+    A = degrade.srconv_matrix(fx["taps"], 64, factor)
+    U, S, V = fx["U"], fx["S"], fx["V"]
+    assert rel_err(U @ torch.diag(S) @ V[:, : S.shape[0]].t(), A) < 1e-5
+    assert rel_err(degrade.srconv_restore(fx["x"], fx["y"], U, S, V), fx["R"]) < 1e-5
+    # size-independent property: A(A^+ y) == y (all singular values non-zero)
+    assert float(S.min()) > 3e-2
+
+
+def test_sampler_steps(golden):
+    fx = golden("sampler_step.pt")
+    ds, inv = _taps(golden)
+    tab = Tables("face_blur", 1000)
+    np.testing.assert_allclose(tab.gammas(1.0, 2.55), fx["gammas"].numpy(), rtol=0, atol=0)
+    restore = lambda v: degrade.blur_restore(v, fx["y"], ds, inv)
+    for t in (99, 50, 1, 0):
+        st = fx["steps"][t]
+        s, x0 = sampler.p_sample_step(tab, fx["x_t"], fx["model_out"], t, st["noise"], restore,
+                                      gamma=st["gamma"], rho=0.25)
+        assert rel_err(x0, st["pred_xstart"]) < 1e-5, t
+        assert rel_err(s, st["sample"]) < 1e-5, t
+    st = fx["steps"]["prev"]
+    s, x0 = sampler.p_sample_step(tab, fx["x_t"], fx["model_out"], 50, st["noise"], restore,
+                                  gamma=fx["steps"][50]["gamma"], rho=0.25, prev_recon=st["prev"], num_frames=2)
+    assert rel_err(x0, st["pred_xstart"]) < 1e-5 and rel_err(s, st["sample"]) < 1e-5
+
+
+def test_sampler_loop(golden):
+    from flair_b200 import synth
+    fx = golden("sampler_loop.pt")
+    ds, inv = _taps(golden)
+    tab = Tables("face_blur", 1000)
+    tape = synth.noise_tape((2, 3, 64, 64), 6, seed=6)
+    restore = lambda v: degrade.blur_restore(v, fx["y"], ds, inv)
+
+    def toy(x, t_in):
+        e = 0.3 * torch.roll(x, 1, -1) - 0.1 * x + 0.001 * float(t_in)
+        return torch.cat([e, torch.zeros_like(e)], 1)
+
+    x5 = sampler.q_sample(tab, fx["hr"], 5, tape[0])
+    assert rel_err(x5, fx["x_start"]) < 1e-6
+    out = sampler.sample_loop(tab, toy, fx["x_start"], tape[1:], restore, rho=0.25, zeta=1.0, noise_level=2.55,
+                              t_start=5)
+    assert rel_err(out, fx["final"]) < 1e-5
