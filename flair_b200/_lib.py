@@ -28,6 +28,19 @@ class ConvParams(C.Structure):
     ]
 
 
+class UpdateParams(C.Structure):
+    _fields_ = [
+        ("x_t", C.c_void_p), ("model_out", C.c_void_p), ("model_ch", C.c_int), ("noise", C.c_void_p),
+        ("R", C.c_void_p), ("q_lr", C.c_void_p), ("up_taps", C.c_void_p),
+        ("up_k", C.c_int), ("sf", C.c_int), ("pre_stride", C.c_int),
+        ("prev", C.c_void_p), ("prev_k", C.c_int), ("frames_per_window", C.c_int),
+        ("coef", C.c_void_p), ("t_arr", C.c_void_p), ("gamma_arr", C.c_void_p), ("x0_in", C.c_void_p),
+        ("t", C.c_int), ("sqrt_one_minus_rho", C.c_float), ("sqrt_rho", C.c_float),
+        ("sample", C.c_void_p), ("pred_xstart", C.c_void_p),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("clip_denoised", C.c_int),
+    ]
+
+
 _lib = None
 
 
@@ -44,6 +57,17 @@ def lib() -> C.CDLL:
         _lib.flair_version.restype = C.c_int
         _lib.flair_check_device.argtypes = [C.c_int]
         _lib.flair_conv_igemm.argtypes = [C.POINTER(ConvParams), C.c_void_p]
+        vp, i, f, ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+        _lib.flair_sampler_update_f32.argtypes = [C.POINTER(UpdateParams), vp]
+        _lib.flair_pred_xstart_f32.argtypes = [vp, vp, i, vp, vp, i, vp, i, i, i, i, vp]
+        _lib.flair_dc_apply_f32.argtypes = [vp, vp, vp, f, vp, i, i, i, i, vp]
+        _lib.flair_mean_variance_f32.argtypes = [vp, vp, vp, i, i, vp, vp, i, vp, vp, vp, i, i, i, vp]
+        _lib.flair_axpby_f32.argtypes = [vp, vp, f, f, vp, ll, vp]
+        _lib.flair_blur_down_f32.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp]
+        _lib.flair_filter_same_f32.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
+        _lib.flair_blur_up_f32.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp]
+        _lib.flair_jpeg_f32.argtypes = [i, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, vp]
+        _lib.flair_sandwich_f32.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp]
     return _lib
 
 

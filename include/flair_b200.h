@@ -94,6 +94,107 @@ typedef struct flair_conv_params {
 
 int flair_conv_igemm(const flair_conv_params* p, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Fused sampler update (fp32).  Replaces gaussian_diffusion.py:344-365,465-470,
+ * 497-515 and the per-step `_extract_into_tensor` uploads (:692-705).
+ * `coef` is a device table [steps][8] = {sqrt_recip_alphas_cumprod,
+ * sqrt_recipm1_alphas_cumprod, sqrt_alphas_cumprod_prev,
+ * sqrt_one_minus_alphas_cumprod_prev, gamma, 0, 0, 0} (float64 tables cast to
+ * fp32 exactly as the reference does after indexing).  The step index comes
+ * from `t_arr` (device int64 per frame, graph-replay friendly) when non-NULL,
+ * else from the host int `t`.
+ * Data-consistency correction: `R` (N,3,H,W) as returned by any restore_fn, or
+ * `q_lr` (N,3,H/sf,W/sf) for the blur operator, in which case
+ * R = Upscale_OP(q_lr) is evaluated in-register (pseudoSR.py:196-225).
+ * ---------------------------------------------------------------------- */
+typedef struct flair_update_params {
+  const float* x_t;        /* (N,3,H,W)                                       */
+  const float* model_out;  /* (N,model_ch,H,W); eps = first 3 channels        */
+  int model_ch;            /* 3 or 6                                          */
+  const float* noise;      /* (N,3,H,W) standard normals (torch generator)    */
+  const float* R;          /* or NULL                                         */
+  const float* q_lr;       /* or NULL                                         */
+  const float* up_taps;    /* (up_k,up_k) = ds_kernel * sf^2                  */
+  int up_k, sf, pre_stride;
+  const float* prev;       /* (B,prev_k,3,H,W) or NULL (prev_recon)           */
+  int prev_k, frames_per_window;
+  const float* coef;
+  const long long* t_arr;  /* per-frame step index (device int64[N]) or NULL */
+  const float* gamma_arr;  /* per-frame gamma (device fp32[N]) or NULL       */
+  const float* x0_in;      /* final pred_xstart supplied by the caller (aux-  */
+                           /* prior path): eps/DC/prev are skipped; or NULL   */
+  int t;                   /* used when t_arr is NULL                         */
+  float sqrt_one_minus_rho, sqrt_rho;
+  float* sample;           /* (N,3,H,W) x_{t-1}                               */
+  float* pred_xstart;      /* (N,3,H,W) or NULL                               */
+  int N, H, W;
+  int clip_denoised;
+} flair_update_params;
+
+int flair_sampler_update_f32(const flair_update_params* p, void* stream);
+/* x0 = clamp(a_t x_t - b_t eps) — gaussian_diffusion.py:311-327,344-349. */
+int flair_pred_xstart_f32(const float* x_t, const float* model_out, int model_ch, const float* coef,
+                          const long long* t_arr, int t, float* x0, int N, int H, int W,
+                          int clip_denoised, void* stream);
+/* out = clamp(x0 - gamma R) — gaussian_diffusion.py:465-470 (generic restore_fn path). */
+int flair_dc_apply_f32(const float* x0, const float* R, const float* gamma_arr, float gamma,
+                       float* out, int N, int H, int W, int clip_denoised, void* stream);
+/* posterior mean + model variance (API parity of p_mean_variance; unused by p_sample) —
+ * gaussian_diffusion.py:226-248,278-309.  tab [steps][8] = {posterior_mean_coef1, coef2,
+ * posterior_log_variance_clipped, log(beta), posterior_variance, posterior_log_variance_clipped,0,0}. */
+int flair_mean_variance_f32(const float* x_t, const float* x0, const float* model_out, int model_ch,
+                            int learned_range, const float* tab, const long long* t_arr, int t,
+                            float* mean, float* variance, float* log_variance, int N, int H, int W,
+                            void* stream);
+/* out = alpha*x + beta*y (q_sample, gaussian_diffusion.py:206-224). */
+int flair_axpby_f32(const float* x, const float* y, float alpha, float beta, float* out,
+                    long long n, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Blur + x4 data-consistency operator pieces (fp32, NCHW planes).
+ * Replaces pseudoSR.py:180-244 (`DownscaleOP`, `Conv_LR_with_Inv_hTh_OP`,
+ * `Upscale_OP`: depth-wise Filter_Layer convs with replication padding).
+ * Taps are the fp32 casts the reference uploads (pseudoSR.py:25-33).
+ * ---------------------------------------------------------------------- */
+/* lr[n,c,m,k] = sum taps[u,v] * x[clamp(sf*m+pre+u-r), clamp(sf*k+pre+v-r)] */
+int flair_blur_down_f32(const float* x, float* lr, const float* taps, int k, int sf, int pre,
+                        int planes, int H, int W, void* stream);
+/* out = replicate-padded k x k cross-correlation at the same resolution,
+ * optionally minus `sub` (same shape): InvhTh(lr) - sub.                  */
+int flair_filter_same_f32(const float* x, const float* sub, float* out, const float* taps, int k,
+                          int planes, int H, int W, void* stream);
+/* hr = Upscale_OP(lr): zero-insert at phase `pre`, replicate pad, k x k.   */
+int flair_blur_up_f32(const float* lr, float* hr, const float* taps, int k, int sf, int pre,
+                      int planes, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------
+ * DCT-domain JPEG (4:2:0 by decimation, 8x8 ortho DCT, QF-scaled tables).
+ * Replaces jpeg.py:72-167 + dct.py:167-202.  `dct`/`idct` are the 8x8
+ * LinearDCT weights built on the host the way the reference builds them.
+ * mode 0: encode  x -> (luma, chroma) quantised coefficient planes
+ * mode 1: decode  (luma, chroma) -> out
+ * mode 2: decode(encode(x)) fused, nothing but `out` is written.
+ * x/out: (N,3,h,w) in [-1,1]; luma (N,1,h,w); chroma (N,2,h/2,w/2); h,w % 16 == 0.
+ * ---------------------------------------------------------------------- */
+int flair_jpeg_f32(int mode, const float* x, float* luma, float* chroma, float* out,
+                   const float* dct, const float* idct, const float* q_luma,
+                   const float* q_chroma, int N, int h, int w, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Separable-SVD bicubic operator (DDRM SRConv).  Replaces
+ * restore_util.py:54-82,162-227 as used by scripts/video_sample.py:177-181:
+ *   R = V1 (V1^T X V1 - G) V1^T  per channel image X (img x img),
+ * V1 = first `small` columns of V (img x small, row-major), G (planes,small,small)
+ * = S^-1 (U^T Y U) S^-1 precomputed per window (may be NULL).
+ * flair_srconv_project: T = V1^T X V1 - G        (planes, small, small)
+ * flair_srconv_expand : R = V1 T V1^T            (planes, img, img)
+ * flair_sandwich_f32  : out = L X Rm (generic small dense product used for setup:
+ *                       L (p,q), X (planes,q,r), Rm (r,s) -> (planes,p,s))
+ * ---------------------------------------------------------------------- */
+int flair_sandwich_f32(const float* L, const float* X, const float* Rm, const float* sub,
+                       float* out, int planes, int p, int q, int r, int s, float* workspace,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
