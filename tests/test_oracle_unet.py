@@ -1,0 +1,36 @@
+"""Pin the CPU oracle of the blur/JPEG UNet against outputs of the reference UNetModel itself
+(tests/golden/unet_blur.pt, made by tools/gen_golden.py unet).  Weights are the deterministic
+synthetic state dict (flair_b200.synth), regenerated here from the recorded key/shape list."""
+import pytest
+import torch
+
+from conftest import rel_err
+from flair_b200 import synth
+from oracle.unet_blur import BlurUNetOracle
+
+
+@pytest.fixture(scope="module")
+def oracle_model(golden):
+    fx = golden("unet_blur.pt")
+    sd = {k: synth.synthetic_tensor(k, shp, 1234) for k, shp in fx["keys"].items()}
+    return BlurUNetOracle(fx["cfg"], sd), fx
+
+
+def test_image_mode(oracle_model):
+    m, fx = oracle_model
+    out = m.forward(fx["x"], fx["image_t"], fx["low_res"][:, None], num_frames=1, enable_cross_frames=False)
+    assert rel_err(out, fx["image_out"]) < 2e-5
+
+
+def test_video_mode(oracle_model):
+    m, fx = oracle_model
+    out = m.forward(fx["x"], fx["video_t"], fx["low_res"][None], num_frames=4, rnn_input=fx["rnn_input"][None],
+                    enable_cross_frames=True, vsrpp_weights=1.0)
+    assert rel_err(out, fx["video_out"]) < 2e-5
+
+
+def test_video_mode_weight_map(oracle_model):
+    m, fx = oracle_model
+    out = m.forward(fx["x"], fx["video_t"], fx["low_res"][None], num_frames=4, rnn_input=None,
+                    enable_cross_frames=True, vsrpp_weights=fx["vsrpp_weights"])
+    assert rel_err(out, fx["video_out_weighted"]) < 2e-5
