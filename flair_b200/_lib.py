@@ -22,6 +22,7 @@ class ConvParams(C.Structure):
         ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("stride_hw", C.c_int),
         ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_stride", C.c_int),
         ("residual", C.c_void_p), ("residual_dtype", C.c_int), ("residual_cstride", C.c_int),
+        ("residual2", C.c_void_p), ("residual2_dtype", C.c_int), ("residual2_cstride", C.c_int),
         ("out", C.c_void_p), ("out_dtype", C.c_int), ("out_layout", C.c_int),
         ("out_cstride", C.c_int), ("act", C.c_int), ("in_dtype", C.c_int),
         ("out_scale", C.c_float), ("gn_partial", C.c_void_p), ("gn_groups", C.c_int),
@@ -38,6 +39,17 @@ class UpdateParams(C.Structure):
         ("t", C.c_int), ("sqrt_one_minus_rho", C.c_float), ("sqrt_rho", C.c_float),
         ("sample", C.c_void_p), ("pred_xstart", C.c_void_p),
         ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("clip_denoised", C.c_int),
+    ]
+
+
+class GNApplyParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("in_dtype", C.c_int), ("out", C.c_void_p), ("out_dtype", C.c_int),
+        ("partial", C.c_void_p), ("nchunks", C.c_int), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("scale", C.c_void_p), ("shift", C.c_void_p), ("film_stride", C.c_int),
+        ("B", C.c_int), ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("groups", C.c_int),
+        ("x_cstride", C.c_int), ("out_cstride", C.c_int),
+        ("norm", C.c_int), ("silu", C.c_int), ("resample", C.c_int), ("eps", C.c_float),
     ]
 
 
@@ -68,6 +80,20 @@ def lib() -> C.CDLL:
         _lib.flair_blur_up_f32.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp]
         _lib.flair_jpeg_f32.argtypes = [i, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, vp]
         _lib.flair_sandwich_f32.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp]
+        _lib.flair_gn_stats_chunks.argtypes = [ll, i]
+        _lib.flair_gn_stats.argtypes = [vp, i, i, ll, i, i, i, vp, i, vp]
+        _lib.flair_gn_apply.argtypes = [C.POINTER(GNApplyParams), vp]
+        _lib.flair_copy_channels.argtypes = [vp, vp, ll, i, i, i, i, i, vp]
+        _lib.flair_attn_spatial.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, vp]
+        _lib.flair_attn_temporal.argtypes = [vp, vp, vp, vp, vp, i, i, ll, i, i, i, vp]
+        _lib.flair_timestep_embedding_f32.argtypes = [vp, vp, vp, i, i, vp]
+        _lib.flair_linear_f32.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+        _lib.flair_pack_im2col6.argtypes = [vp, vp, vp, i, i, i, i, vp]
+        _lib.flair_flow_warp.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, vp]
+        _lib.flair_flow_compose_f32.argtypes = [vp, vp, vp, i, i, i, vp]
+        _lib.flair_planes_to_cl.argtypes = [vp, vp, i, i, i, i, i, i, i, vp]
+        _lib.flair_deform_im2col.argtypes = [vp, vp, i, i, vp, i, i, vp, vp, vp, i, i, i, i, i, f, i, vp]
+        _lib.flair_scale_pixels.argtypes = [vp, vp, ll, i, i, i, vp]
     return _lib
 
 

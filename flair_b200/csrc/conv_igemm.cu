@@ -49,6 +49,9 @@ struct ConvKArgs {
   const void* residual;
   int residual_dtype;
   long long residual_cstride;
+  const void* residual2;
+  int residual2_dtype;
+  long long residual2_cstride;
   void* out;
   int out_dtype, out_layout;
   long long out_cstride;
@@ -81,6 +84,46 @@ __device__ __forceinline__ float2 unpack16(uint32_t u, int dtype) {
     return __half22float2(v);
   }
   return unpack_bf16x2(u);
+}
+
+// v[j] += residual[off + j] for the 16 columns of one accumulator chunk
+__device__ __forceinline__ void add_residual(float (&v)[16], const void* base, int dtype, long long off,
+                                             bool full16, int remaining) {
+  if (dtype == FLAIR_F32) {
+    const float* rp = static_cast<const float*>(base) + off;
+    if (full16) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(rp) + q);
+        v[4 * q + 0] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
+      }
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (j < remaining) v[j] += __ldg(rp + j);
+    }
+  } else {
+    const uint16_t* rp = static_cast<const uint16_t*>(base) + off;
+    if (full16) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack16(uu[e], dtype);
+          v[8 * q + 2 * e] += f.x;
+          v[8 * q + 2 * e + 1] += f.y;
+        }
+      }
+    } else {
+      for (int j = 0; j < 16; ++j) {
+        if (j < remaining) {
+          const uint32_t u = rp[j];
+          v[j] += unpack16(u, dtype).x;
+        }
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -244,44 +287,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], a.act) * a.out_scale;
 
         const bool full16 = (n + 16 <= a.Cout);
-        if (a.residual != nullptr && valid) {
-          if (a.residual_dtype == FLAIR_F32) {
-            const float* rp = static_cast<const float*>(a.residual) + pix * a.residual_cstride + n;
-            if (full16) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 f = __ldg(reinterpret_cast<const float4*>(rp) + q);
-                v[4 * q + 0] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
-              }
-            } else {
-              for (int j = 0; j < 16; ++j)
-                if (n + j < a.Cout) v[j] += __ldg(rp + j);
-            }
-          } else {
-            const uint16_t* rp =
-                static_cast<const uint16_t*>(a.residual) + pix * a.residual_cstride + n;
-            if (full16) {
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
-                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack16(uu[e], a.residual_dtype);
-                  v[8 * q + 2 * e] += f.x;
-                  v[8 * q + 2 * e + 1] += f.y;
-                }
-              }
-            } else {
-              for (int j = 0; j < 16; ++j) {
-                if (n + j < a.Cout) {
-                  const uint32_t u = rp[j];
-                  v[j] += unpack16(u, a.residual_dtype).x;
-                }
-              }
-            }
-          }
-        }
+        if (a.residual != nullptr && valid)
+          add_residual(v, a.residual, a.residual_dtype, pix * a.residual_cstride + n, full16, a.Cout - n);
+        if (a.residual2 != nullptr && valid)
+          add_residual(v, a.residual2, a.residual2_dtype, pix * a.residual2_cstride + n, full16, a.Cout - n);
         if (!valid) continue;
         if (a.out_layout == FLAIR_OUT_NCHW) {
           // fp32 planar output: (frame, n, h, w); lanes walk w -> coalesced per channel
@@ -417,6 +426,8 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   a.bias = p->bias; a.rowbias = p->rowbias; a.rowbias_stride = p->rowbias_stride;
   a.residual = p->residual; a.residual_dtype = p->residual_dtype;
   a.residual_cstride = p->residual_cstride;
+  a.residual2 = p->residual2; a.residual2_dtype = p->residual2_dtype;
+  a.residual2_cstride = p->residual2_cstride;
   a.out = p->out; a.out_dtype = p->out_dtype; a.out_layout = p->out_layout;
   a.out_cstride = p->out_cstride; a.act = p->act;
   a.out_scale = (p->out_scale == 0.0f) ? 1.0f : p->out_scale;

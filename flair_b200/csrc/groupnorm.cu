@@ -1,0 +1,312 @@
+// GroupNorm32 statistics + fused normalise / FiLM / SiLU / 2x resample, channels-last.
+//
+// Replaces guided_diffusion/nn_new.py:17-19 (GroupNorm32: fp32 statistics, eps 1e-5) wrapped in
+// LazyReshaper3D (nn.py:359-367: statistics over (C/G, T, H, W) of one batch element), the
+// `nn.SiLU()` that follows every norm (unet_new.py:237-240,265-268), the scale-shift conditioning
+// h = norm(h) * (1 + scale) + shift (unet_new.py:321-325) and the nearest-x2 / 2x2-average
+// resampling applied to the activated tensor inside up/down ResBlocks (unet_new.py:249-254,310-315).
+// One HBM pass for the statistics (2 B/element read), one for apply (2 B read + 2 B written);
+// the reference spends >= 3 fp32 passes per norm (cast, native_group_norm, SiLU, cast).
+//
+// Layout: x[b][p][c], p = (t,h,w) pixel index, c fastest.  Group g owns channels [g*cpg,(g+1)*cpg).
+#include "common.cuh"
+#include "../../include/flair_b200.h"
+
+namespace {
+
+constexpr int kGroupsMax = 32;
+
+__device__ __forceinline__ void load8(const void* base, long long elem_off, int dtype, float (&v)[8]) {
+  if (dtype == FLAIR_F32) {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem_off);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(base) + elem_off));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f;
+      if (dtype == FLAIR_F16) {
+        __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+        f = __half22float2(h);
+      } else {
+        f = unpack_bf16x2(w[i]);
+      }
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void store8(void* base, long long elem_off, int dtype, const float (&v)[8]) {
+  if (dtype == FLAIR_F32) {
+    float4* p = reinterpret_cast<float4*>(static_cast<float*>(base) + elem_off);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 u;
+    if (dtype == FLAIR_F16) {
+      __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+      __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+      u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+    } else {
+      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    }
+    *reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + elem_off) = u;
+  }
+}
+
+// ---------------------------------------------------------------- statistics (partial sums)
+// grid (nchunks, B); block = vecs * ppb threads (vecs = C/8).  partial[b][chunk][g] = (sum, sumsq).
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const void* __restrict__ x, int dtype, long long P, int C, int cstride, int groups,
+                int ppb, long long pix_per_chunk, float2* __restrict__ partial) {
+  extern __shared__ float sm[];  // [2][ppb][C]
+  const int vecs = C / 8;
+  const int cv = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const long long p0 = chunk * pix_per_chunk;
+  long long p1 = p0 + pix_per_chunk;
+  if (p1 > P) p1 = P;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  const long long base = static_cast<long long>(b) * P;
+  for (long long p = p0 + pl; p < p1; p += ppb) {
+    float v[8];
+    load8(x, (base + p) * cstride + cv * 8, dtype, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+  }
+  float* sS = sm;
+  float* sQ = sm + ppb * C;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sS[pl * C + cv * 8 + j] = s[j];
+    sQ[pl * C + cv * 8 + j] = q[j];
+  }
+  __syncthreads();
+  // fixed-order (deterministic) reduction: per channel over ppb rows, then per group over channels
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, d = 0.f;
+    for (int r = 0; r < ppb; ++r) { a += sS[r * C + c]; d += sQ[r * C + c]; }
+    sS[c] = a; sQ[c] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int cpg = C / groups;
+    float a = 0.f, d = 0.f;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { a += sS[c]; d += sQ[c]; }
+    partial[(static_cast<long long>(b) * gridDim.x + chunk) * groups + threadIdx.x] = make_float2(a, d);
+  }
+}
+
+struct ApplyArgs {
+  const void* x; int in_dtype;
+  void* out; int out_dtype;
+  const float2* partial; int nchunks;
+  const float* gamma; const float* beta;
+  const float* scale; const float* shift; int film_stride;  // per frame rows, or NULL
+  int T, H, W, C, groups;
+  int x_cstride, out_cstride;
+  int norm, silu, resample;  // resample: 0 none, 1 nearest x2 up, 2 2x2 average down
+  float eps;
+};
+
+// grid (blocks, B)
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ ApplyArgs a) {
+  __shared__ float s_mean[kGroupsMax], s_rstd[kGroupsMax];
+  const int b = blockIdx.y;
+  const int cpg = a.C / a.groups;
+  if (a.norm && threadIdx.x < a.groups) {
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < a.nchunks; ++k) {
+      const float2 v = __ldg(a.partial + (static_cast<long long>(b) * a.nchunks + k) * a.groups + threadIdx.x);
+      s += v.x; q += v.y;
+    }
+    const double n = static_cast<double>(a.T) * a.H * a.W * cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  }
+  __syncthreads();
+  const int vecs = a.C / 8;
+  // iteration space: input pixels for "none"/"up", output pixels for "down"
+  const int Hi = (a.resample == 2) ? a.H / 2 : a.H;
+  const int Wi = (a.resample == 2) ? a.W / 2 : a.W;
+  const long long items = static_cast<long long>(a.T) * Hi * Wi * vecs;
+  const long long in_frame = static_cast<long long>(a.H) * a.W;
+  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(it % vecs);
+    long long pix = it / vecs;
+    const int w = static_cast<int>(pix % Wi); pix /= Wi;
+    const int h = static_cast<int>(pix % Hi);
+    const int t = static_cast<int>(pix / Hi);
+    const int c0 = cv * 8;
+    float g[8], be[8], sc[8], sh[8], mu[8], rs[8];
+    if (a.norm) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        g[j] = __ldg(a.gamma + c0 + j); be[j] = __ldg(a.beta + c0 + j);
+        const int grp = (c0 + j) / cpg;
+        mu[j] = s_mean[grp]; rs[j] = s_rstd[grp];
+      }
+      if (a.scale != nullptr) {
+        const long long row = (static_cast<long long>(b) * a.T + t) * a.film_stride;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = 1.0f + __ldg(a.scale + row + c0 + j); sh[j] = __ldg(a.shift + row + c0 + j); }
+      }
+    }
+    auto xform = [&](float (&v)[8]) {
+      if (a.norm) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = (v[j] - mu[j]) * rs[j] * g[j] + be[j];
+          if (a.scale != nullptr) y = y * sc[j] + sh[j];
+          v[j] = y;
+        }
+      }
+      if (a.silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+      }
+    };
+    const long long in_base = (static_cast<long long>(b) * a.T + t) * in_frame;
+    if (a.resample == 2) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float v[8];
+          load8(a.x, (in_base + static_cast<long long>(2 * h + dy) * a.W + 2 * w + dx) * a.x_cstride + c0,
+                a.in_dtype, v);
+          xform(v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+      const long long o = ((static_cast<long long>(b) * a.T + t) * Hi + h) * Wi + w;
+      store8(a.out, o * a.out_cstride + c0, a.out_dtype, acc);
+    } else {
+      float v[8];
+      load8(a.x, (in_base + static_cast<long long>(h) * a.W + w) * a.x_cstride + c0, a.in_dtype, v);
+      xform(v);
+      if (a.resample == 1) {
+        const int Wo = 2 * a.W;
+        const long long ob = (static_cast<long long>(b) * a.T + t) * (4 * in_frame);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx)
+            store8(a.out, (ob + static_cast<long long>(2 * h + dy) * Wo + 2 * w + dx) * a.out_cstride + c0,
+                   a.out_dtype, v);
+      } else {
+        store8(a.out, (in_base + static_cast<long long>(h) * a.W + w) * a.out_cstride + c0, a.out_dtype, v);
+      }
+    }
+  }
+}
+
+// dst[p][coff + c] = src[p][c]   (channel concat into a wider channels-last buffer)
+__global__ void __launch_bounds__(256)
+copy_channels_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long P, int vecs,
+                     int src_vstride, int dst_vstride, int dst_voff) {
+  const long long items = P * vecs;
+  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = it / vecs;
+    const int v = static_cast<int>(it % vecs);
+    dst[p * dst_vstride + dst_voff + v] = __ldg(src + p * src_vstride + v);
+  }
+}
+
+int ew_blocks(long long items, int per_sm) {
+  long long blocks = ceil_div_ll(items, 256);
+  const long long cap = static_cast<long long>(flair_num_sms()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace
+
+extern "C" int flair_gn_stats_chunks(long long pixels_per_batch, int C) {
+  // enough CTAs to fill the machine, at least ~64 pixels per thread-row
+  const int vecs = C / 8;
+  int ppb = 256 / vecs;
+  if (ppb < 1) ppb = 1;
+  if (ppb > 32) ppb = 32;
+  long long chunks = pixels_per_batch / (static_cast<long long>(ppb) * 16);
+  if (chunks < 1) chunks = 1;
+  if (chunks > 296) chunks = 296;
+  return static_cast<int>(chunks);
+}
+
+extern "C" int flair_gn_stats(const void* x, int dtype, int B, long long P, int C, int cstride, int groups,
+                              float* partial, int nchunks, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(x && partial, "flair_gn_stats: null pointer");
+  FLAIR_REQUIRE(groups > 0 && groups <= kGroupsMax && C % groups == 0 && C % 8 == 0 && C <= 2048,
+                "flair_gn_stats: unsupported C=%d groups=%d", C, groups);
+  FLAIR_REQUIRE(cstride % 8 == 0 && cstride >= C, "flair_gn_stats: bad channel stride %d", cstride);
+  FLAIR_REQUIRE(nchunks > 0 && B > 0 && B < 65536, "flair_gn_stats: bad grid");
+  const int vecs = C / 8;
+  int ppb = 256 / vecs;
+  if (ppb < 1) ppb = 1;
+  if (ppb > 32) ppb = 32;
+  const long long ppc = ceil_div_ll(P, nchunks);
+  const size_t smem = sizeof(float) * 2 * ppb * C;
+  dim3 grid(nchunks, B);
+  gn_stats_kernel<<<grid, vecs * ppb, smem, stream>>>(x, dtype, P, C, cstride, groups, ppb, ppc,
+                                                     reinterpret_cast<float2*>(partial));
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int flair_gn_apply(const flair_gn_apply_params* p, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(p && p->x && p->out, "flair_gn_apply: null pointer");
+  FLAIR_REQUIRE(p->C % 8 == 0 && p->x_cstride % 8 == 0 && p->out_cstride % 8 == 0, "flair_gn_apply: C must be a multiple of 8");
+  if (p->norm)
+    FLAIR_REQUIRE(p->partial && p->gamma && p->beta && p->groups > 0 && p->groups <= kGroupsMax &&
+                      p->C % p->groups == 0 && p->nchunks > 0,
+                  "flair_gn_apply: bad normalisation arguments");
+  FLAIR_REQUIRE(p->resample >= 0 && p->resample <= 2, "flair_gn_apply: resample must be 0, 1 or 2");
+  if (p->resample == 2) FLAIR_REQUIRE(p->H % 2 == 0 && p->W % 2 == 0, "flair_gn_apply: odd size for 2x2 pooling");
+  ApplyArgs a{};
+  a.x = p->x; a.in_dtype = p->in_dtype; a.out = p->out; a.out_dtype = p->out_dtype;
+  a.partial = reinterpret_cast<const float2*>(p->partial); a.nchunks = p->nchunks;
+  a.gamma = p->gamma; a.beta = p->beta; a.scale = p->scale; a.shift = p->shift; a.film_stride = p->film_stride;
+  a.T = p->T; a.H = p->H; a.W = p->W; a.C = p->C; a.groups = p->groups > 0 ? p->groups : 1;
+  a.x_cstride = p->x_cstride; a.out_cstride = p->out_cstride;
+  a.norm = p->norm; a.silu = p->silu; a.resample = p->resample; a.eps = p->eps > 0 ? p->eps : 1e-5f;
+  const int Hi = (p->resample == 2) ? p->H / 2 : p->H, Wi = (p->resample == 2) ? p->W / 2 : p->W;
+  const long long items = static_cast<long long>(p->T) * Hi * Wi * (p->C / 8);
+  dim3 grid(ew_blocks(items, 8), p->B);
+  gn_apply_kernel<<<grid, 256, 0, stream>>>(a);
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int flair_copy_channels(const void* src, void* dst, long long pixels, int channels, int elem_bytes,
+                                   int src_cstride, int dst_cstride, int dst_coffset, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(src && dst, "flair_copy_channels: null pointer");
+  const int epv = 16 / elem_bytes;  // elements per 16-byte vector
+  FLAIR_REQUIRE((elem_bytes == 2 || elem_bytes == 4) && channels % epv == 0 && src_cstride % epv == 0 &&
+                    dst_cstride % epv == 0 && dst_coffset % epv == 0,
+                "flair_copy_channels: channel counts/offsets must be multiples of %d", epv);
+  const int vecs = channels / epv;
+  copy_channels_kernel<<<ew_blocks(pixels * vecs, 8), 256, 0, stream>>>(
+      static_cast<const uint4*>(src), static_cast<uint4*>(dst), pixels, vecs, src_cstride / epv,
+      dst_cstride / epv, dst_coffset / epv);
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}

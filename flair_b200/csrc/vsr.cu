@@ -1,0 +1,287 @@
+// BasicVSR++ support kernels on channels-last maps: flow-guided bilinear warping, flow
+// composition, modulated deformable im2col (second-order alignment), per-pixel scaling.
+//
+// Replaces mmedit `flow_warp` (F.grid_sample bilinear, zeros padding, align_corners=True) as used
+// at guided_diffusion/unet_new.py:706,718-719, the offset/mask post-processing of
+// SecondOrderDeformableAlignment.forward (unet_new.py:874-887: 10*tanh residual + flipped flow,
+// sigmoid mask) and the sampling half of torchvision.ops.deform_conv2d (unet_new.py:889-898;
+// the contraction half runs on tcgen05 through flair_conv_igemm over the im2col map), and the
+// in-place `feat_prop *= weight` (unet_new.py:739).
+//
+// Flows are fp32 planes [N][2][H][W] (x displacement, y displacement) as SPyNet produces them.
+#include "common.cuh"
+#include "../../include/flair_b200.h"
+
+namespace {
+
+__device__ __forceinline__ void ld8(const uint16_t* p, int dtype, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f;
+    if (dtype == FLAIR_F16) {
+      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      f = __half22float2(h);
+    } else {
+      f = unpack_bf16x2(w[i]);
+    }
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8(uint16_t* p, int dtype, const float (&v)[8]) {
+  uint4 u;
+  if (dtype == FLAIR_F16) {
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+  } else {
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  }
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// out[n][h][w][coff + c] = bilinear(x[n], (w + fx, h + fy)), zeros outside (grid_sample semantics)
+__global__ void __launch_bounds__(256)
+flow_warp_kernel(const uint16_t* __restrict__ x, const float* __restrict__ flow, uint16_t* __restrict__ out, int N,
+                 int H, int W, int C, int x_cstride, int out_cstride, int dtype) {
+  const int vecs = C / 8;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long items = static_cast<long long>(N) * hw * vecs;
+  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(it % vecs);
+    const long long pix = it / vecs;
+    const long long n = pix / hw;
+    const long long off = pix - n * hw;
+    const int h = static_cast<int>(off / W), w = static_cast<int>(off % W);
+    const float sx = w + __ldg(flow + (n * 2 + 0) * hw + off);
+    const float sy = h + __ldg(flow + (n * 2 + 1) * hw + off);
+    const float fx0 = floorf(sx), fy0 = floorf(sy);
+    const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
+    const float ax = sx - fx0, ay = sy - fy0;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int xx = x0 + dx, yy = y0 + dy;
+        if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+        const float wgt = (dx ? ax : 1.f - ax) * (dy ? ay : 1.f - ay);
+        float v[8];
+        ld8(x + (n * hw + static_cast<long long>(yy) * W + xx) * x_cstride + cv * 8, dtype, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, v[j], acc[j]);
+      }
+    st8(out + pix * out_cstride + cv * 8, dtype, acc);
+  }
+}
+
+// out = f1 + warp(f2, f1)   (fp32 planes [N][2][H][W]) — unet_new.py:718
+__global__ void __launch_bounds__(256)
+flow_compose_kernel(const float* __restrict__ f2, const float* __restrict__ f1, float* __restrict__ out, int N, int H,
+                    int W) {
+  const long long hw = static_cast<long long>(H) * W;
+  const long long items = static_cast<long long>(N) * hw;
+  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = it / hw, off = it - n * hw;
+    const int h = static_cast<int>(off / W), w = static_cast<int>(off % W);
+    const float u = __ldg(f1 + (n * 2) * hw + off), v = __ldg(f1 + (n * 2 + 1) * hw + off);
+    const float sx = w + u, sy = h + v;
+    const float fx0 = floorf(sx), fy0 = floorf(sy);
+    const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
+    const float ax = sx - fx0, ay = sy - fy0;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int xx = x0 + dx, yy = y0 + dy;
+        if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+        const float wgt = (dx ? ax : 1.f - ax) * (dy ? ay : 1.f - ay);
+        const long long o = static_cast<long long>(yy) * W + xx;
+        a0 = fmaf(wgt, __ldg(f2 + (n * 2) * hw + o), a0);
+        a1 = fmaf(wgt, __ldg(f2 + (n * 2 + 1) * hw + o), a1);
+      }
+    out[(n * 2) * hw + off] = u + a0;
+    out[(n * 2 + 1) * hw + off] = v + a1;
+  }
+}
+
+// dst[pix][coff + c] = (16-bit) src[n][c][h][w]    (few channels: flows into the offset-net input)
+__global__ void __launch_bounds__(256)
+planes_to_cl_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int N, int Cs, long long hw,
+                    int dst_cstride, int dst_coff, int dtype) {
+  const long long items = static_cast<long long>(N) * hw * Cs;
+  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(it % Cs);
+    const long long pix = it / Cs;
+    const long long n = pix / hw, off = pix - n * hw;
+    const float v = __ldg(src + (n * Cs + c) * hw + off);
+    uint16_t bits;
+    if (dtype == FLAIR_F16) {
+      __half hv = __float2half_rn(v);
+      bits = *reinterpret_cast<uint16_t*>(&hv);
+    } else {
+      __nv_bfloat16 bv = __float2bfloat16_rn(v);
+      bits = *reinterpret_cast<uint16_t*>(&bv);
+    }
+    dst[pix * dst_cstride + dst_coff + c] = bits;
+  }
+}
+
+// Modulated deformable im2col, 3x3, pad 1, stride 1, dg deform groups over the 2C input channels
+// (first C from xa, last C from xb).  om: [N][H][W][om_cstride] 16-bit raw offset-net output with
+// channel blocks o1 (dg/2*18) | o2 (dg/2*18) | mask (dg*9)  (th.chunk(out, 3), unet_new.py:877).
+// cols: [N*H*W][9 * 2C], column = tap*2C + ci.
+__global__ void __launch_bounds__(256)
+deform_im2col_kernel(const uint16_t* __restrict__ xa, const uint16_t* __restrict__ xb, int xa_cstride, int xb_cstride,
+                     const uint16_t* __restrict__ om, int om_cstride, int om_dtype, const float* __restrict__ flow1,
+                     const float* __restrict__ flow2, uint16_t* __restrict__ cols, int N, int H, int W, int C, int dg,
+                     float mrm, int dtype) {
+  const int cpg = 2 * C / dg;       // channels per deform group (8 or 16)
+  const int vpg = cpg / 8;          // 16-byte vectors per group
+  const int half_g = dg / 2;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long items = static_cast<long long>(N) * hw * 9 * dg * vpg;
+  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = it;
+    const int vi = static_cast<int>(r % vpg); r /= vpg;
+    const int g = static_cast<int>(r % dg); r /= dg;
+    const int tap = static_cast<int>(r % 9); r /= 9;
+    const long long pix = r;
+    const long long n = pix / hw, off = pix - n * hw;
+    const int h = static_cast<int>(off / W), w = static_cast<int>(off % W);
+    const uint16_t* orow = om + pix * om_cstride;
+    auto rd = [&](int ch) -> float {
+      const uint16_t b = __ldg(orow + ch);
+      if (om_dtype == FLAIR_F16) return __half2float(*reinterpret_cast<const __half*>(&b));
+      return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&b));
+    };
+    // offset channel (g*9 + tap)*2 + {0: dy, 1: dx} inside cat(o1, o2); flow.flip(1) = (fy, fx)
+    const int oc = (g * 9 + tap) * 2;
+    const bool second = g >= half_g;
+    const float* fl = second ? flow2 : flow1;
+    const float dy = mrm * tanhf(rd(oc)) + __ldg(fl + (n * 2 + 1) * hw + off);
+    const float dx = mrm * tanhf(rd(oc + 1)) + __ldg(fl + (n * 2 + 0) * hw + off);
+    const float mk = 1.0f / (1.0f + __expf(-rd(dg * 18 + g * 9 + tap)));
+    const float sy = h + tap / 3 - 1 + dy, sx = w + tap % 3 - 1 + dx;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (sy > -1.f && sy < H && sx > -1.f && sx < W) {  // torchvision bilinear_interpolate bounds
+      const float fy0 = floorf(sy), fx0 = floorf(sx);
+      const int y0 = static_cast<int>(fy0), x0 = static_cast<int>(fx0);
+      const float ay = sy - fy0, ax = sx - fx0;
+      const int cg = g * cpg + vi * 8;  // channel inside the 2C concat
+      const uint16_t* src = second ? xb : xa;
+      const int cs = second ? xb_cstride : xa_cstride;
+      const int cl = second ? cg - C : cg;
+#pragma unroll
+      for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+        for (int xx = 0; xx < 2; ++xx) {
+          const int py = y0 + yy, px = x0 + xx;
+          if (py < 0 || py > H - 1 || px < 0 || px > W - 1) continue;
+          const float wgt = (yy ? ay : 1.f - ay) * (xx ? ax : 1.f - ax);
+          float v[8];
+          ld8(src + (n * hw + static_cast<long long>(py) * W + px) * cs + cl, dtype, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, v[j], acc[j]);
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= mk;
+    }
+    st8(cols + pix * (18LL * C) + static_cast<long long>(tap) * 2 * C + g * cpg + vi * 8, dtype, acc);
+  }
+}
+
+// x[pix][c] *= wmap[pix]   (wmap fp32 [N][H][W])
+__global__ void __launch_bounds__(256)
+scale_pixels_kernel(uint16_t* __restrict__ x, const float* __restrict__ wmap, long long pixels, int C, int cstride,
+                    int dtype) {
+  const int vecs = C / 8;
+  const long long items = pixels * vecs;
+  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = it / vecs;
+    const int cv = static_cast<int>(it % vecs);
+    const float s = __ldg(wmap + pix);
+    float v[8];
+    uint16_t* p = x + pix * cstride + cv * 8;
+    ld8(p, dtype, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= s;
+    st8(p, dtype, v);
+  }
+}
+
+int blocks_for(long long items) {
+  long long b = ceil_div_ll(items, 256);
+  const long long cap = static_cast<long long>(flair_num_sms()) * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+extern "C" int flair_flow_warp(const void* x, const float* flow, void* out, int N, int H, int W, int C,
+                               int x_cstride, int out_cstride, int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(x && flow && out && C % 8 == 0 && x_cstride % 8 == 0 && out_cstride % 8 == 0, "flair_flow_warp: bad arguments");
+  flow_warp_kernel<<<blocks_for(static_cast<long long>(N) * H * W * (C / 8)), 256, 0, stream>>>(
+      static_cast<const uint16_t*>(x), flow, static_cast<uint16_t*>(out), N, H, W, C, x_cstride, out_cstride, dtype);
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int flair_flow_compose_f32(const float* f2, const float* f1, float* out, int N, int H, int W, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(f2 && f1 && out, "flair_flow_compose_f32: null pointer");
+  flow_compose_kernel<<<blocks_for(static_cast<long long>(N) * H * W), 256, 0, stream>>>(f2, f1, out, N, H, W);
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int flair_planes_to_cl(const float* src, void* dst, int N, int Cs, int H, int W, int dst_cstride,
+                                  int dst_coffset, int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(src && dst, "flair_planes_to_cl: null pointer");
+  const long long hw = static_cast<long long>(H) * W;
+  planes_to_cl_kernel<<<blocks_for(N * hw * Cs), 256, 0, stream>>>(src, static_cast<uint16_t*>(dst), N, Cs, hw,
+                                                                  dst_cstride, dst_coffset, dtype);
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int flair_deform_im2col(const void* xa, const void* xb, int xa_cstride, int xb_cstride, const void* om,
+                                   int om_cstride, int om_dtype, const float* flow1, const float* flow2, void* cols,
+                                   int N, int H, int W, int C, int deform_groups, float max_residue_magnitude,
+                                   int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(xa && xb && om && flow1 && flow2 && cols, "flair_deform_im2col: null pointer");
+  FLAIR_REQUIRE(deform_groups > 0 && deform_groups % 2 == 0 && (2 * C) % deform_groups == 0 &&
+                    ((2 * C) / deform_groups) % 8 == 0,
+                "flair_deform_im2col: channels per deform group must be a multiple of 8 (C=%d, dg=%d)", C, deform_groups);
+  const long long items = static_cast<long long>(N) * H * W * 9 * deform_groups * ((2 * C / deform_groups) / 8);
+  deform_im2col_kernel<<<blocks_for(items), 256, 0, stream>>>(
+      static_cast<const uint16_t*>(xa), static_cast<const uint16_t*>(xb), xa_cstride, xb_cstride,
+      static_cast<const uint16_t*>(om), om_cstride, om_dtype, flow1, flow2, static_cast<uint16_t*>(cols), N, H, W, C,
+      deform_groups, max_residue_magnitude, dtype);
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int flair_scale_pixels(void* x, const float* wmap, long long pixels, int C, int cstride, int dtype,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(x && wmap && C % 8 == 0, "flair_scale_pixels: bad arguments");
+  scale_pixels_kernel<<<blocks_for(pixels * (C / 8)), 256, 0, stream>>>(static_cast<uint16_t*>(x), wmap, pixels, C,
+                                                                       cstride, dtype);
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}

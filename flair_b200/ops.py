@@ -26,11 +26,11 @@ def _ptr(t):
 def _cstride(t: torch.Tensor) -> int:
     """Per-pixel channel stride of a channels-last [B,T,H,W,C] view."""
     assert t.dim() == 5 and t.stride(4) == 1, "expected channels-last [B,T,H,W,C]"
-    cs = t.stride(3)
     B, T, H, W, _ = t.shape
-    assert t.stride(2) == cs * W and t.stride(1) == cs * W * H and t.stride(0) == cs * W * H * T, (
-        "feature map must be pixel-contiguous (only the channel stride may be padded)"
-    )
+    cs = t.stride(3) if W > 1 else (t.stride(2) if H > 1 else t.shape[4])
+    ok = (H == 1 or t.stride(2) == cs * W) and (T == 1 or t.stride(1) == cs * W * H) and \
+        (B == 1 or t.stride(0) == cs * W * H * T)  # strides of size-1 dims are meaningless
+    assert ok, "feature map must be pixel-contiguous (only the channel stride may be padded)"
     return cs
 
 
@@ -54,7 +54,7 @@ def pack_conv_weight(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
     return out.contiguous()
 
 
-def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, residual=None, out=None,
+def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, residual=None, residual2=None, out=None,
          out_dtype=None, act=L.ACT_NONE, stride=1, nchw_out=False, out_scale=1.0):
     """Implicit-GEMM convolution (see flair_conv_igemm in include/flair_b200.h).
 
@@ -69,6 +69,8 @@ def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, residual=Non
         else:
             out = torch.empty(B, T, Ho, Wo, cout, dtype=out_dtype or x.dtype, device=x.device)
     p = L.ConvParams()
+    if kt == 1:  # frames are independent: let M-tiles span them (matters at 4x4 .. 16x16 maps)
+        B, T = 1, B * T
     p.x = _ptr(x); p.B, p.T, p.H, p.W, p.Cin = B, T, H, W, cin
     p.x_cstride = _cstride(x)
     p.wgt = _ptr(wpk); p.Cout = cout
@@ -81,6 +83,10 @@ def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, residual=Non
         p.residual = _ptr(residual)
         p.residual_dtype = _DT[residual.dtype]
         p.residual_cstride = _cstride(residual)
+    if residual2 is not None:
+        p.residual2 = _ptr(residual2)
+        p.residual2_dtype = _DT[residual2.dtype]
+        p.residual2_cstride = _cstride(residual2)
     p.out = _ptr(out)
     p.out_dtype = _DT[out.dtype]
     p.out_layout = L.OUT_NCHW if nchw_out else L.OUT_NHWC
@@ -247,3 +253,147 @@ def sandwich(Lm, X, Rm, sub=None):
     L.check(L.lib().flair_sandwich_f32(_ptr(Lm), _ptr(X), _ptr(Rm), _ptr(sub), _ptr(out), planes, p_, q, r, s_,
                                        _ptr(ws), _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# UNet building blocks on channels-last [B,T,H,W,C] maps
+# ----------------------------------------------------------------------------------------------
+def gn_stats(x, groups=32):
+    """Partial GroupNorm sums over (T,H,W,C/G) per batch element: returns (partial, nchunks)."""
+    B, T, H, W, Cc = x.shape
+    P = T * H * W
+    n = L.lib().flair_gn_stats_chunks(P, Cc)
+    partial = torch.empty(B, n, groups, 2, dtype=torch.float32, device=x.device)
+    L.check(L.lib().flair_gn_stats(_ptr(x), _DT[x.dtype], B, P, Cc, _cstride(x), groups, _ptr(partial), n, _stream()))
+    return partial, n
+
+
+def gn_apply(x, stats=None, gamma=None, beta=None, *, scale=None, shift=None, silu=False, resample=0,
+             out_dtype=None, groups=32, out=None):
+    """Fused normalise (+FiLM) (+SiLU) (+2x resample).  stats=None -> plain resample / cast."""
+    B, T, H, W, Cc = x.shape
+    Ho, Wo = {0: (H, W), 1: (2 * H, 2 * W), 2: (H // 2, W // 2)}[resample]
+    if out is None:
+        out = torch.empty(B, T, Ho, Wo, Cc, dtype=out_dtype or x.dtype, device=x.device)
+    p = L.GNApplyParams()
+    p.x = _ptr(x); p.in_dtype = _DT[x.dtype]; p.out = _ptr(out); p.out_dtype = _DT[out.dtype]
+    if stats is not None:
+        partial, n = stats
+        p.partial = _ptr(partial); p.nchunks = n; p.gamma = _ptr(gamma); p.beta = _ptr(beta); p.norm = 1
+        if scale is not None:
+            assert scale.stride(0) == shift.stride(0) and scale.stride(1) == 1
+            p.scale = _ptr(scale); p.shift = _ptr(shift); p.film_stride = scale.stride(0)
+    p.B, p.T, p.H, p.W, p.C, p.groups = B, T, H, W, Cc, groups
+    p.x_cstride = _cstride(x); p.out_cstride = _cstride(out)
+    p.silu = int(silu); p.resample = resample; p.eps = 1e-5
+    L.check(L.lib().flair_gn_apply(C.byref(p), _stream()))
+    return out
+
+
+def concat_channels(a, b):
+    """th.cat([a, b], channel) for channels-last maps."""
+    B, T, H, W, Ca = a.shape
+    Cb = b.shape[-1]
+    out = torch.empty(B, T, H, W, Ca + Cb, dtype=a.dtype, device=a.device)
+    pix = B * T * H * W
+    es = a.element_size()
+    L.check(L.lib().flair_copy_channels(_ptr(a), _ptr(out), pix, Ca, es, _cstride(a), Ca + Cb, 0, _stream()))
+    L.check(L.lib().flair_copy_channels(_ptr(b), _ptr(out), pix, Cb, es, _cstride(b), Ca + Cb, Ca, _stream()))
+    return out
+
+
+def copy_channels_into(src, dst, coffset):
+    B, T, H, W, Cs = src.shape
+    L.check(L.lib().flair_copy_channels(_ptr(src), _ptr(dst), B * T * H * W, Cs, src.element_size(), _cstride(src),
+                                        _cstride(dst), coffset, _stream()))
+
+
+def attn_spatial(qkv, heads, rowbias=None):
+    """qkv [B,T,H,W,3C] head-major (H,3,64) -> [B,T,H,W,C]; attention over the H*W tokens of each frame."""
+    B, T, H, W, C3 = qkv.shape
+    Cc = C3 // 3
+    out = torch.empty(B, T, H, W, Cc, dtype=qkv.dtype, device=qkv.device)
+    L.check(L.lib().flair_attn_spatial(_ptr(qkv), _ptr(out), _ptr(rowbias), 0 if rowbias is None else rowbias.stride(0),
+                                       B * T, H * W, heads, _cstride(qkv), Cc, _DT[qkv.dtype], _stream()))
+    return out
+
+
+def attn_temporal(qkv, cq, ck, bv, frames):
+    B, T, H, W, C3 = qkv.shape
+    Cc = C3 // 3
+    assert qkv.is_contiguous()
+    out = torch.empty(B, T, H, W, Cc, dtype=qkv.dtype, device=qkv.device)
+    L.check(L.lib().flair_attn_temporal(_ptr(qkv), _ptr(out), _ptr(cq), _ptr(ck), _ptr(bv), B, T, H * W, Cc, frames,
+                                        _DT[qkv.dtype], _stream()))
+    return out
+
+
+def timestep_embedding(t, freqs):
+    t = t.float().contiguous()
+    out = torch.empty(t.shape[0], 2 * freqs.shape[0], dtype=torch.float32, device=t.device)
+    L.check(L.lib().flair_timestep_embedding_f32(_ptr(t), _ptr(freqs), _ptr(out), t.shape[0], 2 * freqs.shape[0], _stream()))
+    return out
+
+
+def linear_f32(x, Wt, bias=None, silu_in=False, silu_out=False):
+    """y = act_out(bias + act_in(x) @ Wt), Wt [K,N] fp32 (small M)."""
+    M, K = x.shape
+    N = Wt.shape[1]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    L.check(L.lib().flair_linear_f32(_ptr(x), _ptr(Wt), _ptr(bias), _ptr(y), M, K, N, int(silu_in), int(silu_out), _stream()))
+    return y
+
+
+def pack_im2col6(a, b, dtype=torch.bfloat16):
+    """cat([a, b], 1) of two (N,3,H,W) fp32 maps -> [1,N,H,W,64] 16-bit im2col map (k = tap*6 + c)."""
+    a, b = _f32c(a), _f32c(b)
+    N, _, H, W = a.shape
+    out = torch.empty(1, N, H, W, 64, dtype=dtype, device=a.device)
+    L.check(L.lib().flair_pack_im2col6(_ptr(a), _ptr(b), _ptr(out), N, H, W, _DT[dtype], _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# BasicVSR++ support (per-frame channels-last maps [N,H,W,C]; flows fp32 [N,2,H,W])
+# ----------------------------------------------------------------------------------------------
+def _cs4(t):
+    N, H, W, _ = t.shape
+    cs = t.stride(2) if W > 1 else (t.stride(1) if H > 1 else t.shape[3])
+    assert t.dim() == 4 and t.stride(3) == 1 and (H == 1 or t.stride(1) == cs * W) \
+        and (N == 1 or t.stride(0) == cs * W * H), "expected pixel-contiguous [N,H,W,C] view"
+    return cs
+
+
+def flow_warp(x, flow, out=None):
+    N, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty(N, H, W, Cc, dtype=x.dtype, device=x.device)
+    L.check(L.lib().flair_flow_warp(_ptr(x), _ptr(flow), _ptr(out), N, H, W, Cc, _cs4(x), _cs4(out), _DT[x.dtype], _stream()))
+    return out
+
+
+def flow_compose(f2, f1):
+    out = torch.empty_like(f1)
+    N, _, H, W = f1.shape
+    L.check(L.lib().flair_flow_compose_f32(_ptr(f2), _ptr(f1), _ptr(out), N, H, W, _stream()))
+    return out
+
+
+def planes_to_cl(src, dst, coffset):
+    N, Cs, H, W = src.shape
+    L.check(L.lib().flair_planes_to_cl(_ptr(src), _ptr(dst), N, Cs, H, W, _cs4(dst), coffset, _DT[dst.dtype], _stream()))
+
+
+def deform_im2col(xa, xb, om, flow1, flow2, deform_groups, mrm):
+    N, H, W, Cc = xa.shape
+    cols = torch.empty(1, N, H, W, 18 * Cc, dtype=xa.dtype, device=xa.device)
+    L.check(L.lib().flair_deform_im2col(_ptr(xa), _ptr(xb), _cs4(xa), _cs4(xb), _ptr(om), _cs4(om), _DT[om.dtype],
+                                        _ptr(flow1), _ptr(flow2), _ptr(cols), N, H, W, Cc, deform_groups, float(mrm),
+                                        _DT[xa.dtype], _stream()))
+    return cols
+
+
+def scale_pixels_(x, wmap):
+    N, H, W, Cc = x.shape
+    L.check(L.lib().flair_scale_pixels(_ptr(x), _ptr(wmap), N * H * W, Cc, _cs4(x), _DT[x.dtype], _stream()))
+    return x

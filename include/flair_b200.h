@@ -80,6 +80,9 @@ typedef struct flair_conv_params {
   const void* residual;/* same geometry as out, or NULL                       */
   int residual_dtype;  /* FLAIR_BF16 / FLAIR_F32 / FLAIR_F16                  */
   int residual_cstride;
+  const void* residual2; /* optional second residual (same dtype/stride rules)  */
+  int residual2_dtype;
+  int residual2_cstride;
   void* out;
   int out_dtype;       /* FLAIR_BF16 / FLAIR_F32 / FLAIR_F16                  */
   int out_layout;      /* FLAIR_OUT_NHWC / FLAIR_OUT_NCHW                     */
@@ -193,6 +196,89 @@ int flair_jpeg_f32(int mode, const float* x, float* luma, float* chroma, float* 
  * ---------------------------------------------------------------------- */
 int flair_sandwich_f32(const float* L, const float* X, const float* Rm, const float* sub,
                        float* out, int planes, int p, int q, int r, int s, float* workspace,
+                       void* stream);
+
+/* ------------------------------------------------------------------------
+ * GroupNorm32 on channels-last maps.  Replaces nn_new.py:17-19 + nn.py:359-367
+ * (statistics over (C/G,T,H,W) per batch element), the SiLU that follows,
+ * the scale-shift conditioning (unet_new.py:321-325) and the 2x resampling of
+ * up/down ResBlocks (unet_new.py:249-254,310-315).
+ *   flair_gn_stats: partial[b][chunk][g] = (sum, sum of squares), fp32
+ *   flair_gn_apply: finishes the statistics and writes
+ *        out = resample( silu?( ((x-mean)*rstd*gamma+beta) * (1+scale) + shift ) )
+ *   (norm = 0 skips the normalisation: plain resample / dtype cast of x).
+ * ---------------------------------------------------------------------- */
+int flair_gn_stats_chunks(long long pixels_per_batch, int C);
+int flair_gn_stats(const void* x, int dtype, int B, long long pixels_per_batch, int C, int cstride,
+                   int groups, float* partial, int nchunks, void* stream);
+typedef struct flair_gn_apply_params {
+  const void* x; int in_dtype;   /* [B][T][H][W][x_cstride]                   */
+  void* out; int out_dtype;      /* [B][T][H'][W'][out_cstride]               */
+  const float* partial; int nchunks;
+  const float* gamma; const float* beta;           /* [C]                     */
+  const float* scale; const float* shift;          /* [B*T][film_stride] or NULL */
+  int film_stride;
+  int B, T, H, W, C, groups;
+  int x_cstride, out_cstride;
+  int norm, silu, resample;      /* resample: 0 none, 1 nearest x2, 2 avg 2x2 */
+  float eps;
+} flair_gn_apply_params;
+int flair_gn_apply(const flair_gn_apply_params* p, void* stream);
+/* dst[p][dst_coffset + c] = src[p][c]: channel concat (th.cat(dim=2), unet_new.py:1359). */
+int flair_copy_channels(const void* src, void* dst, long long pixels, int channels, int elem_bytes,
+                        int src_cstride, int dst_cstride, int dst_coffset, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Attention.  Spatial: QKVAttentionLegacy (unet_new.py:540-570), qkv channels
+ * head-major (H,3,64), fp32 online softmax, optional per-frame channel bias
+ * (AttentionbottleBlock emb term, unet_new.py:426-428).  Temporal: windowed
+ * 1 x (F-1) attention of TemporalAttention (unet_new.py:473-517, nn.py:370-394)
+ * over per-frame projections qkv = [q|k|v] with the positional constants
+ * cq = Wq pe_mid + bq [C], ck = Wk pe_j + bk [F-1][C], bv [C] folded in.
+ * ---------------------------------------------------------------------- */
+int flair_attn_spatial(const void* qkv, void* out, const float* rowbias, int rowbias_stride, int N,
+                       int L, int heads, int qkv_cstride, int out_cstride, int dtype, void* stream);
+int flair_attn_temporal(const void* qkv, void* out, const float* cq, const float* ck, const float* bv,
+                        int B, int T, long long pixels, int C, int frames, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Conditioning path (fp32) and input packing.
+ * flair_timestep_embedding_f32: nn_new.py:103-121 (freqs table from the host).
+ * flair_linear_f32: y = act_out(bias + act_in(x) Wt), Wt is [K][N] (time_embed
+ *   unet_new.py:979-984 and all ResBlock emb_layers :258-264 concatenated).
+ * flair_pack_im2col6: cat([a,b], channel) (N,3,H,W) fp32 x2 -> [N][H][W][64]
+ *   16-bit im2col (k = tap*6 + c) feeding the first conv (unet_new.py:993,1331).
+ * ---------------------------------------------------------------------- */
+int flair_timestep_embedding_f32(const float* t, const float* freqs, float* out, int N, int dim,
+                                 void* stream);
+int flair_linear_f32(const float* x, const float* Wt, const float* bias, float* y, int M, int K, int N,
+                     int silu_in, int silu_out, void* stream);
+int flair_pack_im2col6(const float* a, const float* b, void* out, int N, int H, int W, int dtype,
+                       void* stream);
+
+/* ------------------------------------------------------------------------
+ * BasicVSR++ support (channels-last maps, fp32 flow planes [N][2][H][W]).
+ * flair_flow_warp      : mmedit flow_warp / F.grid_sample bilinear, zeros padding,
+ *                        align_corners=True (unet_new.py:706,719).
+ * flair_flow_compose_f32: f1 + warp(f2, f1) (unet_new.py:718).
+ * flair_planes_to_cl   : fp32 planes -> 16-bit channel slice (flows into the
+ *                        offset-net input, unet_new.py:875).
+ * flair_deform_im2col  : offset/mask post-processing (unet_new.py:877-887) +
+ *                        sampling half of torchvision.ops.deform_conv2d (:889-898);
+ *                        cols [N*H*W][9*2C], column = tap*2C + channel; the GEMM
+ *                        half is flair_conv_igemm with a 1x1 kernel over 18C.
+ * flair_scale_pixels   : feat_prop *= weight (unet_new.py:739).
+ * ---------------------------------------------------------------------- */
+int flair_flow_warp(const void* x, const float* flow, void* out, int N, int H, int W, int C,
+                    int x_cstride, int out_cstride, int dtype, void* stream);
+int flair_flow_compose_f32(const float* f2, const float* f1, float* out, int N, int H, int W, void* stream);
+int flair_planes_to_cl(const float* src, void* dst, int N, int Cs, int H, int W, int dst_cstride,
+                       int dst_coffset, int dtype, void* stream);
+int flair_deform_im2col(const void* xa, const void* xb, int xa_cstride, int xb_cstride, const void* om,
+                        int om_cstride, int om_dtype, const float* flow1, const float* flow2, void* cols,
+                        int N, int H, int W, int C, int deform_groups, float max_residue_magnitude,
+                        int dtype, void* stream);
+int flair_scale_pixels(void* x, const float* wmap, long long pixels, int C, int cstride, int dtype,
                        void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,103 @@
+"""CPU-side checks of the drop-in boundary: module tree / state-dict names, host-side operator
+preparation, schedule tables, and that the C-ABI library loads and exports every declared symbol.
+No kernel is launched here."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from flair_b200 import _lib as L
+    lib = L.lib()
+    header = (ROOT / "include" / "flair_b200.h").read_text()
+    names = set(re.findall(r"\b(flair_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 25
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/flair_b200.h but not exported"
+    assert lib.flair_version() == 100
+
+
+def test_no_gpu_is_a_loud_error():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from flair_b200 import _lib as L
+    assert L.lib().flair_check_device(0) != 0
+    assert b"no CUDA device" in L.lib().flair_last_error()
+
+
+def test_unet_state_dict_matches_reference(golden):
+    """Same 1638 keys and shapes as the reference UNetModel (so its checkpoints load)."""
+    from guided_diffusion.unet_new import UNetModel
+    fx = golden("unet_blur.pt")
+    model = UNetModel(**fx["cfg"], use_fp16=True, use_checkpoint=True)
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert set(mine) == set(fx["keys"]), (sorted(set(mine) ^ set(fx["keys"]))[:10])
+    assert mine == fx["keys"]
+    model.convert_to_fp16()
+    sd = model.state_dict()
+    assert sd["input_blocks.1.0.in_layers.2.wrapped_module.weight"].dtype == torch.float16
+    assert sd["input_blocks.1.0.in_layers.0.wrapped_module.weight"].dtype == torch.float32
+    assert sd["input_blocks.13.3.wrapped_module.q_linear.weight"].dtype == torch.float16
+    assert sd["out.2.wrapped_module.weight"].dtype == torch.float32
+
+
+def test_unet_refuses_cpu_tensors(golden):
+    from guided_diffusion.unet_new import UNetModel
+    fx = golden("unet_blur.pt")
+    cfg = dict(fx["cfg"], channel_mult=(0.5, 1), attention_resolutions=(), rnn_resolutions=())
+    model = UNetModel(**cfg)
+    with pytest.raises(RuntimeError, match="B200 only"):
+        model(torch.zeros(1, 3, 64, 64), torch.zeros(1, dtype=torch.long), low_res_input=torch.zeros(1, 1, 3, 64, 64),
+              num_frames=1)
+
+
+def test_blur_operator_host_preparation(golden):
+    from guided_diffusion import pseudoSR as P
+    g = golden("pseudosr_taps.pt")
+    host = P.pseudoSR(P.Get_pseudoSR_Conf(4), upscale_kernel=g["raw_kernel"].numpy().astype(np.float32), kernel_indx=10)
+    assert host.ds_kernel.shape == (9, 9) and host.inv_hTh.shape == (39, 39)
+    np.testing.assert_array_equal(host.ds_kernel, g["ds_kernel"].numpy())
+    np.testing.assert_array_equal(host.inv_hTh, g["inv_hTh"].numpy())
+    op = host.WrapArchitecture_PyTorch()
+    assert torch.equal(op.DownscaleOP.Filter_OP.weight[0, 0], g["w_down"])
+    assert torch.equal(op.Conv_LR_with_Inv_hTh_OP.Filter_OP.weight[0, 0], g["w_inv"])
+    assert torch.equal(op.Upscale_OP.Filter_OP.weight[0, 0], g["w_up"])
+    assert list(op.pre_stride) == [1, 1] and list(op.post_stride) == [2, 2]
+
+
+def test_jpeg_tables(golden):
+    from guided_diffusion import jpeg
+    from guided_diffusion.dct import linear_dct_weight
+    fx = golden("dc_jpeg.pt")
+    q1, q2 = jpeg.general_quant_matrix(fx["qf"])
+    assert torch.equal(q1.reshape(8, 8), fx["q_luma"]) and torch.equal(q2.reshape(8, 8), fx["q_chroma"])
+    assert torch.equal(linear_dct_weight(8, "dct"), fx["dct"]) and torch.equal(linear_dct_weight(8, "idct"), fx["idct"])
+
+
+@pytest.mark.parametrize("task,name,n", [("gaussian", "face_blur", 1000), ("bicubic", "face_bicubic", 2000)])
+def test_spaced_diffusion_tables(golden, task, name, n):
+    from guided_diffusion import gaussian_diffusion as gd
+    from guided_diffusion.respace import SpacedDiffusion, space_timesteps
+    ref = golden("schedule.pt")[task]
+    d = SpacedDiffusion(use_timesteps=space_timesteps(n, "100", "uniform"), betas=gd.get_named_beta_schedule(name, n),
+                        noise_schedule=name, model_mean_type=gd.ModelMeanType.EPSILON,
+                        model_var_type=gd.ModelVarType.FIXED_SMALL, loss_type=gd.LossType.MSE)
+    assert d.timestep_map == ref["timestep_map"].tolist() and d.num_timesteps == 100
+    for k in ("betas", "sqrt_alphas_cumprod_prev", "sqrt_one_minus_alphas_cumprod_prev", "sqrt_recip_alphas_cumprod",
+              "sqrt_recipm1_alphas_cumprod"):
+        np.testing.assert_array_equal(getattr(d, k), ref[k].numpy(), err_msg=k)
+
+
+def test_space_timesteps_variants():
+    from guided_diffusion.respace import space_timesteps
+    assert space_timesteps(1000, "ddim50") == set(range(0, 1000, 20))
+    assert space_timesteps(300, [10, 15, 20]) == space_timesteps(300, "10,15,20")
+    assert len(space_timesteps(300, [10, 15, 20])) == 45
+    with pytest.raises(ValueError):
+        space_timesteps(10, "20")
