@@ -97,6 +97,10 @@ def lib() -> C.CDLL:
     return _lib
 
 
+LAUNCHES = [0]  # C-ABI launch calls issued (graph replays add the launches they captured)
+
+
 def check(rc: int) -> None:
+    LAUNCHES[0] += 1
     if rc != 0:
         raise RuntimeError(f"flair_b200: {lib().flair_last_error().decode()} (rc={rc})")

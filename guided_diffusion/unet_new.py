@@ -699,6 +699,8 @@ class UNetModel(nn.Module):
                                  zero_module(LazyReshaper2D(conv_nd(dims, input_ch, out_channels, 3, padding=1))))
         self._flow_cache = {}
         self._emb_pack = None
+        self._graphs = {}
+        self.use_cuda_graph = True
 
     # ------------------------------------------------------------------ dtype helpers (reference :1224-1254)
     def _torso_apply(self, fn, lin_dtype):
@@ -767,22 +769,75 @@ class UNetModel(nn.Module):
     @th.no_grad()
     def forward(self, x, timesteps, low_res_input=None, num_frames=None, rnn_input=None, enable_cross_frames=True,
                 vsrpp_weights=None, **kwargs):
-        """x (B*T,3,H,W) fp32, timesteps (B*T,), low_res_input (B,T,3,H,W) -> (B*T,out_channels,H,W) fp32."""
+        """x (B*T,3,H,W) fp32, timesteps (B*T,), low_res_input (B,T,3,H,W) -> (B*T,out_channels,H,W) fp32.
+
+        With `use_cuda_graph` (default) the ~5000 kernel launches of one forward are captured once per
+        input signature and replayed: inputs are copied into static buffers, flows into static flow
+        buffers, and the result is returned as a fresh tensor."""
         if not x.is_cuda:
             raise RuntimeError("guided_diffusion.unet_new.UNetModel runs on a B200 only (no CPU fallback)")
-        N, _, H, W = x.shape
         T = int(num_frames)
+        cross = bool(enable_cross_frames)
+        flows = {}
+        if cross and self.need_flows_res and any(isinstance(m, BasicVSRPP) for m in self.modules()):
+            flows = self._flows(low_res_input if rnn_input is None else rnn_input, T)
+        if not self.use_cuda_graph or th.cuda.is_current_stream_capturing():
+            return self._forward_impl(x, timesteps, low_res_input, T, flows, cross, vsrpp_weights)
+        return self._forward_graphed(x, timesteps, low_res_input, T, flows, cross, vsrpp_weights)
+
+    def _param_stamp(self):
+        return hash(tuple((p.data_ptr(), p._version) for p in self.parameters()))
+
+    def _forward_graphed(self, x, timesteps, low, T, flows, cross, weights):
+        wkey = ("t", tuple(weights.shape)) if th.is_tensor(weights) else ("s", weights)
+        key = (tuple(x.shape), str(x.device), T, cross, wkey, self.compute_dtype, self.stream_dtype,
+               tuple(sorted(flows)), timesteps.dtype)
+        stamp = self._param_stamp()
+        if self._graphs.get("stamp") != stamp:
+            self._graphs = {"stamp": stamp}
+        g = self._graphs.get(key)
+        if g is None:
+            st = dict(x=x.float().clone(), t=timesteps.clone(), low=low.float().clone(),
+                      flows={r: tuple(f.clone() for f in ff) for r, ff in flows.items()},
+                      w=weights.float().clone() if th.is_tensor(weights) else weights)
+            run = lambda: self._forward_impl(st["x"], st["t"], st["low"], T, st["flows"], cross, st["w"])
+            side = th.cuda.Stream()
+            side.wait_stream(th.cuda.current_stream())
+            with th.cuda.stream(side):  # warm-up: packs weights, sets kernel attributes, sizes the pool
+                run()
+            th.cuda.current_stream().wait_stream(side)
+            graph = th.cuda.CUDAGraph()
+            n0 = L.LAUNCHES[0]
+            with th.cuda.graph(graph):
+                st["out"] = run()
+            g = dict(graph=graph, st=st, flow_src=None, launches=L.LAUNCHES[0] - n0)
+            if len(self._graphs) > 8:
+                self._graphs = {"stamp": stamp}
+            self._graphs[key] = g
+        st = g["st"]
+        st["x"].copy_(x)
+        st["t"].copy_(timesteps)
+        st["low"].copy_(low)
+        if th.is_tensor(weights):
+            st["w"].copy_(weights)
+        if flows and g["flow_src"] is not self._flow_cache.get("flows"):
+            for r, ff in flows.items():
+                for dst, src in zip(st["flows"][r], ff):
+                    dst.copy_(src)
+            g["flow_src"] = self._flow_cache.get("flows")
+        g["graph"].replay()
+        L.LAUNCHES[0] += g["launches"]
+        return st["out"].clone()
+
+    def _forward_impl(self, x, timesteps, low_res_input, T, flows, cross, vsrpp_weights):
+        N, _, H, W = x.shape
         B = N // T
         dt = self.compute_dtype
         ew = self._emb_weights()
         emb0 = ops.linear_f32(timestep_embedding(timesteps, self.model_channels), ew["w0"], ew["b0"], silu_out=True)
         emb = ops.linear_f32(emb0, ew["w2"], ew["b2"])
         emb_all = ops.linear_f32(emb, ew["wall"], ew["ball"], silu_in=True)
-        flows = {}
-        if enable_cross_frames and self.need_flows_res and any(
-                isinstance(m, BasicVSRPP) for m in self.modules()):
-            flows = self._flows(low_res_input if rnn_input is None else rnn_input, T)
-        ctx = _Ctx(emb_all, flows, vsrpp_weights, bool(enable_cross_frames), dt, T, self.stream_dtype)
+        ctx = _Ctx(emb_all, flows, vsrpp_weights, cross, dt, T, self.stream_dtype)
 
         conv_in = self.input_blocks[0][0].wrapped_module
         st = (dt, conv_in.weight.data_ptr(), conv_in.weight._version)
@@ -803,7 +858,7 @@ class UNetModel(nn.Module):
         n_out, c_out = self.out[0].wrapped_module, self.out[2].wrapped_module
         st = (dt, c_out.weight.data_ptr(), c_out.weight._version)
         if getattr(self, "_out_stamp", None) != st:
-            self._out_pk = (_w(c_out, dt), _f(c_out.bias))
+            self._out_pk = (_w(c_out, dt), _f(c_out.bias), _f(n_out.weight), _f(n_out.bias))
             self._out_stamp = st
-        a = ops.gn_apply(h, ops.gn_stats(h), _f(n_out.weight), _f(n_out.bias), silu=True, out_dtype=dt)
+        a = ops.gn_apply(h, ops.gn_stats(h), self._out_pk[2], self._out_pk[3], silu=True, out_dtype=dt)
         return ops.conv(a, self._out_pk[0], self.out_channels, (1, 3, 3), bias=self._out_pk[1], nchw_out=True)

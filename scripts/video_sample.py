@@ -1,0 +1,175 @@
+"""FLAIR video restoration demo on the B200-native path — same entry points, config dictionaries and
+constants as the reference's scripts/video_sample.py (`main`, `gaussian_demo`, `jpeg_demo`,
+`x8_bicubic_demo`, `x16_bicubic_demo`, `get_A_func`, DIFFUSION_CONFIG / MODEL_TYPE / MODEL_CONFIG /
+INIT_FUNC / CKPT_PATH / RESTORE_FUNC, FRAME_SLICE_LEN, OVERLAP).
+
+Differences that are deliberate:
+  * the windowing / sampling loop lives in flair_b200.pipeline (shared with bench.py);
+  * `image_size` is a parameter (the reference hard-wires 512);
+  * the auxiliary CodeFormer face prior and facelib are out of scope (BASELINE.json north_star): when
+    their checkpoints / packages are absent the sampler runs with `aux_model=None`, which is the
+    reference's behaviour for w = 1;
+  * cyclopts is optional (argparse fallback with the same sub-command spellings).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+from copy import deepcopy
+from functools import partial
+from pathlib import Path
+
+sys.path.append(f"{Path(__file__).parent.parent.resolve()}")
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from flair_b200 import pipeline
+from guided_diffusion.gaussian_diffusion import LossType, ModelMeanType, ModelVarType, get_named_beta_schedule
+from guided_diffusion.jpeg import jpeg_decode, jpeg_encode
+from guided_diffusion.respace import SpacedDiffusion, space_timesteps
+from guided_diffusion.sr3 import UNet as BicubicUNet
+from guided_diffusion.unet_new import UNetModel as BlurUNet
+
+torch.set_grad_enabled(False)
+
+_EPS_FIXED = dict(model_mean_type=ModelMeanType.EPSILON, model_var_type=ModelVarType.FIXED_SMALL,
+                  loss_type=LossType.MSE, rescale_timesteps=False)
+_EPS_LEARNED = dict(model_mean_type=ModelMeanType.EPSILON, model_var_type=ModelVarType.LEARNED_RANGE,
+                    loss_type=LossType.RESCALED_MSE, rescale_timesteps=False)
+DIFFUSION_CONFIG = {
+    "x8_bicubic": dict(diffusion_steps=2000, noise_schedule="face_bicubic", **_EPS_FIXED),
+    "x16_bicubic": dict(diffusion_steps=2000, noise_schedule="face_bicubic", **_EPS_FIXED),
+    "gaussian": dict(diffusion_steps=1000, noise_schedule="face_blur", **_EPS_LEARNED),
+    "jpeg": dict(diffusion_steps=1000, noise_schedule="face_blur", **_EPS_LEARNED),
+}
+MODEL_TYPE = {"x8_bicubic": BicubicUNet, "x16_bicubic": BicubicUNet, "gaussian": BlurUNet, "jpeg": BlurUNet}
+_SR3 = dict(image_size=512, in_channel=6, out_channel=3, inner_channel=64, norm_groups=16,
+            channel_mults=(1, 2, 4, 8, 16), attn_res=(64, 32), vsrpp_res=(512, 256), spatial_attn=False,
+            temporal_attn=True, res_blocks=1, dropout=0.0, dtype=torch.float16, cross_frame_module=True,
+            use_checkpoint=True, num_frames=7, head_dim=64)
+_BLUR = dict(image_size=512, in_channels=6, model_channels=128, out_channels=6, num_res_blocks=2,
+             attention_resolutions=(512 // 32, 512 // 16, 512 // 8), rnn_resolutions=(1, 2),
+             channel_mult=(0.5, 1, 1, 2, 2, 4, 4), use_fp16=True, num_head_channels=64, resblock_updown=True,
+             use_scale_shift_norm=True, temporal_block=True, use_checkpoint=True)
+MODEL_CONFIG = {"x8_bicubic": dict(_SR3), "x16_bicubic": dict(_SR3), "gaussian": dict(_BLUR), "jpeg": dict(_BLUR)}
+INIT_FUNC = {t: partial(pipeline.init_frames, t, size=512) for t in MODEL_CONFIG}
+CKPT_PATH = {"x8_bicubic": "./checkpoints/flair_x8_bicubic.pt", "x16_bicubic": "./checkpoints/flair_x16_bicubic.pt",
+             "gaussian": "./checkpoints/flair_gaussian.pt", "jpeg": "./checkpoints/flair_jpeg.pt",
+             "codeformer": "./checkpoints/codeformer.pth"}
+DEFAULT_WEIGHT = 1.0
+FRAME_SLICE_LEN = pipeline.FRAME_SLICE_LEN
+OVERLAP = pipeline.OVERLAP
+
+
+def bicubic_restore(x, d, A_func):
+    return A_func.restore(x, d.reshape(-1, *d.shape[-3:]))
+
+
+def gaussian_restore(x, d, A_func, jpeg_qf=-1):
+    return pipeline.BlurRestore(A_func, d, jpeg_qf)(x)
+
+
+RESTORE_FUNC = {"x8_bicubic": bicubic_restore, "x16_bicubic": bicubic_restore, "gaussian": gaussian_restore,
+                "jpeg": gaussian_restore}
+
+
+def _blur_kernel():
+    mat = Path("./miscs/kernels_12.mat")
+    if mat.exists():
+        from scipy.io import loadmat
+        return np.asarray(loadmat(str(mat))["kernels"][0, 3], dtype=np.float32)
+    return np.load(Path(pipeline.__file__).parent / "data" / "blur_kernel_k03.npy")
+
+
+def get_A_func(task, device, image_size=512):
+    return pipeline.make_operator(task, device, image_size, kernels_mat=_blur_kernel()
+                                  if task in ("gaussian", "jpeg") else None)
+
+
+def _read_frames(video_path):
+    import cv2
+    import re
+    nat = lambda p: [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", p.name)]
+    paths = sorted(Path(video_path).glob("*.[jJpP][pPnN][gG]"), key=nat)
+    print(f"found {len(paths)} frames")
+    return torch.stack([torch.from_numpy(cv2.cvtColor(cv2.imread(str(p)), cv2.COLOR_BGR2RGB).transpose(2, 0, 1)).float()
+                        / 255 for p in paths])
+
+
+def main(task, video_path, output_path, device=torch.device("cuda"), t_start=-1, jpeg_qf=-1, w=0.5, tau=5,
+         aligned=False, rho=0.5, noise_level=12.75, zeta=-1, image_size=512, weights="checkpoint", seed=None):
+    """Restore the frames under `video_path` and write PNGs to `output_path` (reference :265-492).
+    `weights="synthetic"` replaces the (offline-unavailable) checkpoint by flair_b200.synth weights."""
+    device = torch.device(device)
+    print(f"task: {task}, video_path: {video_path}, output_dir: {output_path}, device: {device}")
+    cfg = deepcopy(DIFFUSION_CONFIG[task])
+    steps = cfg.pop("diffusion_steps")
+    cfg["use_timesteps"] = space_timesteps(steps, "100", "uniform")
+    cfg["betas"] = get_named_beta_schedule(cfg.get("noise_schedule"), steps)
+    diffusion = SpacedDiffusion(**cfg)
+    mcfg = dict(MODEL_CONFIG[task], image_size=image_size)
+    if task in ("gaussian", "jpeg") and image_size != 512:
+        mcfg["attention_resolutions"] = (16, 32, 64)
+    model = MODEL_TYPE[task](**mcfg).to(device)
+    model.convert_to_fp16()
+    model.eval()
+    if weights == "synthetic":
+        from flair_b200 import synth
+        model.load_state_dict(synth.synthetic_state_dict(model))
+    else:
+        model.load_state_dict(torch.load(CKPT_PATH[task], map_location="cpu"))
+    if w != 1.0 and not os.path.exists(CKPT_PATH["codeformer"]):
+        print("codeformer checkpoint not found: running without the auxiliary face prior (aux_model=None)")
+    frames = _read_frames(video_path).to(device)
+    A_func = get_A_func(task, device, image_size)
+    knobs = pipeline.TaskKnobs(rho=rho, noise_level=noise_level, zeta=zeta, jpeg_qf=jpeg_qf,
+                               factor=pipeline.KNOBS[task].factor)
+    gen = None if seed is None else torch.Generator(device=device).manual_seed(seed)
+    out = pipeline.restore_clip(model, diffusion, A_func, task, frames, image_size=image_size, chained=True,
+                                knobs=knobs, generator=gen, t_start=t_start)
+    import cv2
+    rec = (out * 255).byte().permute(0, 2, 3, 1).cpu().numpy()
+    os.makedirs(output_path, exist_ok=True)
+    for i, frame in enumerate(rec):
+        cv2.imwrite(str(Path(output_path) / f"{i:04d}.png"), cv2.cvtColor(frame, cv2.COLOR_RGB2BGR))
+    return out
+
+
+def x8_bicubic_demo(device=torch.device("cuda"), **kw):
+    return main(task="x8_bicubic", video_path=Path("./data/x8_bicubic"), output_path=Path("./output/x8_bicubic"),
+                device=device, w=0.85, rho=0.85, noise_level=0.0, **kw)
+
+
+def x16_bicubic_demo(device=torch.device("cuda"), **kw):
+    return main(task="x16_bicubic", video_path=Path("./data/x16_bicubic"), output_path=Path("./output/x16_bicubic"),
+                device=device, w=0.7, rho=0.85, noise_level=0.0, **kw)
+
+
+def gaussian_demo(device=torch.device("cuda"), **kw):
+    return main(task="gaussian", video_path=Path("./data/gaussian"), output_path=Path("./output/gaussian"),
+                device=device, w=0.75, rho=0.25, noise_level=2.55, zeta=1.0, **kw)
+
+
+def jpeg_demo(device=torch.device("cuda"), **kw):
+    return main(task="jpeg", video_path=Path("./data/jpeg"), output_path=Path("./output/jpeg"), device=device,
+                w=0.5, rho=0.5, noise_level=12.75, zeta=1.0, jpeg_qf=60, **kw)
+
+
+_COMMANDS = {"x8-bicubic-demo": x8_bicubic_demo, "x16-bicubic-demo": x16_bicubic_demo,
+             "gaussian-demo": gaussian_demo, "jpeg-demo": jpeg_demo}
+
+
+def app(argv=None):
+    p = argparse.ArgumentParser(description="FLAIR video restoration (B200-native)")
+    p.add_argument("command", choices=sorted(_COMMANDS))
+    p.add_argument("--device", default="cuda")
+    p.add_argument("--image-size", type=int, default=512)
+    p.add_argument("--weights", choices=["checkpoint", "synthetic"], default="checkpoint")
+    a = p.parse_args(argv)
+    _COMMANDS[a.command](device=torch.device(a.device), image_size=a.image_size, weights=a.weights)
+
+
+if __name__ == "__main__":
+    app()

@@ -7,7 +7,8 @@ from guided_diffusion.unet_new import UNetModel
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 mode = sys.argv[2] if len(sys.argv) > 2 else "video"
-cfg = dict(image_size=256, in_channels=6, model_channels=128, out_channels=6, num_res_blocks=2,
+SZ = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+cfg = dict(image_size=SZ, in_channels=6, model_channels=128, out_channels=6, num_res_blocks=2,
            attention_resolutions=(16, 32, 64), rnn_resolutions=(1, 2), channel_mult=(0.5, 1, 1, 2, 2, 4, 4),
            use_fp16=True, num_head_channels=64, resblock_updown=True, use_scale_shift_norm=True,
            temporal_block=True, use_checkpoint=True)
@@ -17,8 +18,8 @@ model.load_state_dict(synth.synthetic_state_dict(model))
 model.convert_to_fp16(); model.eval().cuda()
 print("model ready", time.time() - t0, flush=True)
 dev = "cuda"
-clip = (synth.synthetic_clip(T, 256) * 2 - 1).to(dev)
-x = torch.randn(T, 3, 256, 256, device=dev)
+clip = (synth.synthetic_clip(T, SZ) * 2 - 1).to(dev)
+x = torch.randn(T, 3, SZ, SZ, device=dev)
 ts = torch.full((T,), 500, device=dev)
 def fwd():
     if mode == "video":
@@ -33,6 +34,6 @@ for _ in range(n): o = fwd()
 e1.record(); torch.cuda.synchronize()
 wall = (time.time() - t0) / n * 1e3
 gpu = e0.elapsed_time(e1) / n
-gf = {"video": 2370.2, "image": 248.0}[mode] * T
+gf = {"video": 2370.2, "image": 248.0}[mode] * T * (SZ / 256) ** 2
 print(f"{mode} T={T}: wall {wall:.1f} ms  device {gpu:.1f} ms  -> {gf/gpu:.1f} TFLOP/s algorithmic; finite={bool(torch.isfinite(o).all())}")
 print("peak mem GB", torch.cuda.max_memory_allocated() / 2**30)

@@ -54,3 +54,78 @@ def main(OUT):
         print(k, tuple(fx[k].shape), float(fx[k].abs().mean()), float(fx[k].std()))
     torch.save(fx, OUT / "unet_blur.pt")
     print("unet fixture written")
+
+
+def sampler_full(OUT, steps_t_start=-1, name="sampler_full.pt"):
+    """Full respaced sampling of one 4-frame 64x64 window with the reference sampler + reference UNet
+    (video mode) + reference blur operator, on a recorded noise tape.  Golden for the 40 dB PSNR target."""
+    import time
+    import numpy as np
+    from scipy.io import loadmat
+    import guided_diffusion.gaussian_diffusion as gd
+    import guided_diffusion.nn as rnn
+    import guided_diffusion.unet_new as runet
+    import guided_diffusion.pseudoSR as rpsr
+    from guided_diffusion.respace import SpacedDiffusion, space_timesteps
+    from torchvision.transforms import functional as VF
+    import torch.nn.functional as F
+    from flair_b200 import synth
+
+    def cpu_attn(self, q, k, v):
+        s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) / math.sqrt(q.shape[-1])
+        return torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, dim=-1), v.float()).to(q.dtype)
+    rnn.FalshAttn.forward = cpu_attn
+    S, T = 64, 4
+    cfg = dict(image_size=S, in_channels=6, model_channels=128, out_channels=6, num_res_blocks=2,
+               attention_resolutions=(16, 32, 64), rnn_resolutions=(1, 2), channel_mult=(0.5, 1, 1, 2, 2, 4, 4),
+               use_fp16=False, num_head_channels=64, resblock_updown=True, use_scale_shift_norm=True,
+               temporal_block=True, use_checkpoint=False)
+    real = torch.cuda.is_available
+    torch.cuda.is_available = lambda: True
+    model = runet.UNetModel(**cfg)
+    torch.cuda.is_available = real
+    model.eval()
+    model.load_state_dict(synth.synthetic_state_dict(model, seed=1234))
+    d = SpacedDiffusion(use_timesteps=space_timesteps(1000, "100", "uniform"),
+                        betas=gd.get_named_beta_schedule("face_blur", 1000), noise_schedule="face_blur",
+                        model_mean_type=gd.ModelMeanType.EPSILON, model_var_type=gd.ModelVarType.LEARNED_RANGE,
+                        loss_type=gd.LossType.RESCALED_MSE, rescale_timesteps=False)
+    kernel = loadmat("/root/reference/miscs/kernels_12.mat")["kernels"]
+    conf = rpsr.Get_pseudoSR_Conf(4); conf.sigmoid_range_limit = False; conf.input_range = np.array(None)
+    A = rpsr.pseudoSR(conf, upscale_kernel=kernel[0, 3], kernel_indx=10).WrapArchitecture_PyTorch()
+    hr = synth.synthetic_clip(T, S, seed=8)
+    lr01 = ((A.DownscaleOP(hr * 2 - 1) + 1) / 2).clamp(0, 1)            # degraded frames in [0,1]
+    # --- exactly the per-window preparation of scripts/video_sample.py:372-425 (HR size S instead of 512)
+    init = (F.interpolate(lr01, (S, S), mode="area").clamp(0, 1) - 0.5) / 0.5
+    degraded = (lr01 - 0.5) / 0.5
+    n_steps = 100 if steps_t_start == -1 else steps_t_start + 1
+    tape = synth.noise_tape((T, 3, S, S), n_steps, seed=2)
+    it = iter(tape[1:])
+    gd.th.randn_like = lambda t: next(it).to(t)
+    t0 = 99 if steps_t_start == -1 else steps_t_start
+    noise = d.q_sample(init, torch.full((T,), t0), noise=tape[0])
+    rnn_in = VF.normalize(VF.resize(VF.normalize(degraded, 0.5, 0.5), (S, S), VF.InterpolationMode.BICUBIC), -1, 2).clamp(-1, 1)
+    kwargs = {"low_res_input": init[None], "num_frames": T, "enable_cross_frames": True, "vsrpp_weights": 1.0,
+              "rnn_input": rnn_in[None]}
+    restore = lambda x: A.A_pinv(degraded, x)
+    t_begin = time.time()
+    sample = d.sample(model, noise, model_kwargs=kwargs, device=torch.device("cpu"), progress=False,
+                      clip_denoised=True, restore_fn=restore, post_fn=None, face_restore_helper=None,
+                      aux_model=lambda *a, **k: None, w=0.75, tau=d.num_timesteps, affine_matrices=None, aligned=False,
+                      sample_mode="ddpm", rho=0.25, noise_level=2.55, prev_recon=None, zeta=1.0, t_start=steps_t_start)
+    print("reference sampling took", time.time() - t_begin, "s; out range", float(sample.min()), float(sample.max()))
+    torch.save({"lr01": lr01, "hr": hr, "sample": sample, "size": S, "frames": T, "t_start": steps_t_start,
+                "noise_seed": 2}, OUT / name)
+
+
+if __name__ == "__main__":
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import ref_env
+    OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+    ref_env.setup()
+    if sys.argv[1] == "full":
+        sampler_full(OUT, -1, "sampler_full.pt")
+    else:
+        sampler_full(OUT, int(sys.argv[1]), f"sampler_t{sys.argv[1]}.pt")
