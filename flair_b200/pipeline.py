@@ -126,7 +126,7 @@ def restore_window(model, diffusion, A, task, lr01, *, image_size, prev_recon=No
     for out in diffusion.p_sample_loop_progressive(
             model, noise.shape, noise=noise, model_kwargs=model_kwargs, device=dev, restore_fn=restore,
             aux_model=None, rho=knobs.rho, noise_level=knobs.noise_level, zeta=knobs.zeta, prev_recon=prev_recon,
-            t_start=t_start, noise_tape=tape):
+            t_start=t_start, noise_tape=tape, generator=generator):
         final = out
     return final["sample"]
 

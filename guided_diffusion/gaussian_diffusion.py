@@ -245,7 +245,8 @@ class GaussianDiffusion:
 
     def p_sample(self, model, x, t, clip_denoised=True, model_kwargs=None, restore_fn=None,
                  affine_matrices=None, face_restore_helper=None, aux_model=None, w=0.5, start_timestep=None,
-                 tau=None, aligned=False, rho=0.35, prev_recon=None, gamma=None, _t_host=None, _noise=None):
+                 tau=None, aligned=False, rho=0.35, prev_recon=None, gamma=None, _t_host=None, _noise=None,
+                 _generator=None):
         """x_t -> {sample: x_{t-1}, pred_xstart} (reference :423-517).
 
         restore_fn may be any callable Tensor->Tensor (protocol of :465-468); callables exposing
@@ -262,7 +263,8 @@ class GaussianDiffusion:
                 raise AssertionError("restore_fn needs gamma (reference p_sample, :466)")
             gamma_arr = gamma.reshape(gamma.shape[0], -1)[:, 0] if th.is_tensor(gamma) else \
                 th.full((x.shape[0],), float(gamma), device=x.device)
-        noise = _noise if _noise is not None else th.randn_like(x)
+        noise = _noise if _noise is not None else (
+            th.randn_like(x) if _generator is None else th.randn(x.shape, device=x.device, generator=_generator))
         frames = None if model_kwargs is None else model_kwargs.get("num_frames")
         prev = None
         if prev_recon is not None:
@@ -334,11 +336,12 @@ class GaussianDiffusion:
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, model_kwargs=None,
                                   device=None, progress=False, affine_matrices=None, face_restore_helper=None,
                                   aux_model=None, restore_fn=None, w=0.5, tau=None, aligned=False, rho=0.35,
-                                  noise_level=None, prev_recon=None, zeta=-1, t_start=-1, noise_tape=None):
+                                  noise_level=None, prev_recon=None, zeta=-1, t_start=-1, noise_tape=None,
+                                  generator=None):
         """Generator over per-step dicts {sample, pred_xstart, t} (reference :589-689).
 
-        `noise_tape` (optional, not in the reference) supplies the per-step normals instead of
-        torch's generator: entry i is used by the i-th executed step (parity runs)."""
+        `noise_tape` / `generator` (optional, not in the reference) supply the per-step normals /
+        the torch generator they are drawn from: entry i is used by the i-th executed step (parity runs)."""
         if device is None:
             device = next(model.parameters()).device
         if not isinstance(shape, (tuple, list, th.Size)):
@@ -371,7 +374,7 @@ class GaussianDiffusion:
                     affine_matrices=affine_matrices, face_restore_helper=face_restore_helper, aux_model=aux_model,
                     w=float(ws[i]), start_timestep=start_timestep, tau=tau, aligned=aligned, rho=rho,
                     prev_recon=prev_recon, gamma=gam_dev[i].expand(n), _t_host=i,
-                    _noise=None if noise_tape is None else noise_tape[step_no])
+                    _noise=None if noise_tape is None else noise_tape[step_no], _generator=generator)
                 img = out["sample"]
                 out["t"] = t
                 yield out
