@@ -15,10 +15,14 @@
 // Weights are packed [tap][Cout_pad][Cin_pad] so a (n_tile x 64) slab of one tap
 // is one 2-D box, also K-major.
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
-// alloc), warps 2..5 = epilogue (one TMEM lane quarter each).  The kernel is
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+// alloc), warps 2..9 = epilogue (two per TMEM lane quarter, splitting the columns).  The epilogue
+// is specialised at compile time on (output type/layout, activation): a runtime-generic version
+// cost ~6k warp-instructions per tile and left the tensor pipe 6 % busy (profiles/r01_conv64_*).  The kernel is
 // persistent: grid = min(#tiles, #SMs); accumulators are double-buffered in
 // TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/flair_b200.h"
 
@@ -27,7 +31,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 x 16-bit = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter (columns split in halves)
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // + TMA warp + MMA warp
 constexpr int kMaxTaps = 27;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
 
@@ -42,6 +47,13 @@ struct ConvKArgs {
   int Cout, Cout_pad;
   int kblocks, ntaps, stride;
   int stages;
+  // mode 0: one (tap, k-block) per pipeline stage, A tile = 128 output pixels.
+  // mode 1: "halo" — 16x8-pixel tiles; one (dt, dw, k-block) per stage loads a 16x10 halo slab of A
+  //         once and issues the three dh taps from it (start address shifted by whole 2 KB row
+  //         groups), cutting A traffic 2.4x.
+  // mode 2: mode 1 + the weights of this CTA's N tile stay resident in shared memory.
+  int mode, ntd;
+  uint32_t a_bytes, b_bytes, stage_bytes, w_bytes;
   int8_t tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dt[kMaxTaps];
   const float* bias;
   const float* rowbias;
@@ -98,6 +110,7 @@ __device__ __forceinline__ void add_residual(float (&v)[16], const void* base, i
         v[4 * q + 0] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
       }
     } else {
+#pragma unroll
       for (int j = 0; j < 16; ++j)
         if (j < remaining) v[j] += __ldg(rp + j);
     }
@@ -116,6 +129,7 @@ __device__ __forceinline__ void add_residual(float (&v)[16], const void* base, i
         }
       }
     } else {
+#pragma unroll
       for (int j = 0; j < 16; ++j) {
         if (j < remaining) {
           const uint32_t u = rp[j];
@@ -126,21 +140,120 @@ __device__ __forceinline__ void add_residual(float (&v)[16], const void* base, i
   }
 }
 
+struct EpiPos {
+  int w, h, n0;
+  bool valid;
+  long long frame, pix;
+};
+
+// One epilogue warp: accumulator columns [col_begin, col_end) of its 32 TMEM lanes, 16 at a time.
+// KIND: 0 fp16 NHWC, 1 bf16 NHWC, 2 fp32 NHWC, 3 fp32 NCHW.  ACT: FLAIR_ACT_*.
+template <int KIND, int ACT>
+__device__ __forceinline__ void epilogue_cols(const ConvKArgs& a, uint32_t t_addr, int col_begin, int col_end,
+                                              const EpiPos& pos, const float* __restrict__ sb) {
+  for (int c0 = col_begin; c0 < col_end; c0 += 16) {
+    uint32_t r[16];
+    __syncwarp();  // tcgen05.ld is warp-collective: reconverge after divergent stores
+    tmem_ld16(t_addr + static_cast<uint32_t>(c0), r);
+    tmem_ld_wait();
+    const int n = pos.n0 + c0;
+    if (n >= a.Cout) continue;  // warp-uniform: padded columns
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 bq = *reinterpret_cast<const float4*>(sb + c0 + 4 * q);
+      v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bq.x;
+      v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq.y;
+      v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq.z;
+      v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq.w;
+    }
+    const bool full16 = (n + 16 <= a.Cout);
+    if (a.rowbias != nullptr && pos.valid) {
+      const float* rb = a.rowbias + pos.frame * a.rowbias_stride + n;
+      if (full16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(rb) + q);
+          v[4 * q + 0] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n + j < a.Cout) v[j] += __ldg(rb + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float y = v[j];
+      if (ACT == FLAIR_ACT_RELU) y = fmaxf(y, 0.0f);
+      else if (ACT == FLAIR_ACT_LRELU01) y = y > 0.0f ? y : 0.1f * y;
+      else if (ACT == FLAIR_ACT_SILU) y = silu_f(y);
+      v[j] = y * a.out_scale;
+    }
+    if (a.residual != nullptr && pos.valid)
+      add_residual(v, a.residual, a.residual_dtype, pos.pix * a.residual_cstride + n, full16, a.Cout - n);
+    if (a.residual2 != nullptr && pos.valid)
+      add_residual(v, a.residual2, a.residual2_dtype, pos.pix * a.residual2_cstride + n, full16, a.Cout - n);
+    if (!pos.valid) continue;
+    if (KIND == 3) {
+      // fp32 planar output: (frame, n, h, w); lanes walk w -> coalesced per channel
+      float* op = static_cast<float*>(a.out);
+      const long long plane = static_cast<long long>(a.Ho) * a.Wo;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n + j < a.Cout)
+          op[(pos.frame * a.Cout + n + j) * plane + static_cast<long long>(pos.h) * a.Wo + pos.w] = v[j];
+    } else if (KIND == 2) {
+      float* op = static_cast<float*>(a.out) + pos.pix * a.out_cstride + n;
+      if (full16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<float4*>(op)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n + j < a.Cout) op[j] = v[j];
+      }
+    } else {
+      constexpr int DT = (KIND == 0) ? FLAIR_F16 : FLAIR_BF16;
+      uint16_t* op = static_cast<uint16_t*>(a.out) + pos.pix * a.out_cstride + n;
+      if (full16) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint4 u;
+          u.x = pack16(v[8 * q + 0], v[8 * q + 1], DT);
+          u.y = pack16(v[8 * q + 2], v[8 * q + 3], DT);
+          u.z = pack16(v[8 * q + 4], v[8 * q + 5], DT);
+          u.w = pack16(v[8 * q + 6], v[8 * q + 7], DT);
+          reinterpret_cast<uint4*>(op)[q] = u;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n + j < a.Cout) op[j] = static_cast<uint16_t>(pack16(v[j], 0.0f, DT) & 0xFFFFu);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvKArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages][A 16 KB][B n_tile*128 B] then barriers
-  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * kBlockK * 2;
-  const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(16) float s_bias[2][256];
+  // carve: [resident weights (mode 2)] [stages][A][B] then barriers
+  const uint32_t b_bytes = a.b_bytes;
+  const uint32_t stage_bytes = a.stage_bytes;
+  uint8_t* smem_w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_w + a.w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(a.stages) * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + a.stages;
   uint64_t* tfull_bar = bars + 2 * a.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* w_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -154,8 +267,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
+    mbar_init(w_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -167,17 +281,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile walk of this CTA: (m_idx, n_idx) = f(local iteration)
+  //   modes 0/1: linear tile id = blockIdx.x + i*gridDim.x, n fastest (neighbouring CTAs share A in L2)
+  //   mode 2   : n_idx fixed per CTA (its weights are resident), m strided by gridDim.x / n_tiles
   const int total_tiles = a.m_tiles * a.n_tiles;
-  const int k_iters = a.ntaps * a.kblocks;
+  const bool resident = (a.mode == 2);
+  const int my_n = resident ? static_cast<int>(blockIdx.x) % a.n_tiles : 0;
+  const int m_first = resident ? static_cast<int>(blockIdx.x) / a.n_tiles : 0;
+  const int m_step = resident ? static_cast<int>(gridDim.x) / a.n_tiles : 0;
+  const int my_tiles = resident ? (m_first < a.m_tiles ? (a.m_tiles - 1 - m_first) / m_step + 1 : 0)
+                                : (static_cast<int>(blockIdx.x) < total_tiles
+                                       ? (total_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
+                                       : 0);
+  auto tile_at = [&](int i, int& m_idx, int& n_idx) {
+    if (resident) { m_idx = m_first + i * m_step; n_idx = my_n; }
+    else { const int tile = blockIdx.x + i * gridDim.x; n_idx = tile % a.n_tiles; m_idx = tile / a.n_tiles; }
+  };
+  const int k_iters = (a.mode == 0) ? a.ntaps * a.kblocks : a.ntd * 3 * a.kblocks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (resident) {  // this CTA's weights: every (tap, k-block) slab of its N tile, once
+        mbar_expect_tx(w_bar, a.w_bytes);
+        for (int tap = 0; tap < a.ntaps; ++tap)
+          for (int kb = 0; kb < a.kblocks; ++kb)
+            tma_load_2d(smem_w + static_cast<size_t>(tap * a.kblocks + kb) * b_bytes, &tmB, w_bar, kb * kBlockK,
+                        tap * a.Cout_pad + my_n * a.n_tile);
+      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_idx = tile % a.n_tiles;
-        int m_idx = tile / a.n_tiles;
+      for (int i = 0; i < my_tiles; ++i) {
+        int m_idx, n_idx;
+        tile_at(i, m_idx, n_idx);
         const int tw = m_idx % a.tiles_w; m_idx /= a.tiles_w;
         const int th = m_idx % a.tiles_h; m_idx /= a.tiles_h;
         const int tt = m_idx % a.tiles_t;
@@ -185,19 +321,42 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int w0 = (tw << a.lbw) * a.stride;
         const int h0 = (th << a.lbh) * a.stride;
         const int t0 = tt << a.lbt;
-        for (int tap = 0; tap < a.ntaps; ++tap) {
-          const int cw = w0 + a.tap_dw[tap];
-          const int ch = h0 + a.tap_dh[tap];
-          const int ct = t0 + a.tap_dt[tap];
-          const int brow = tap * a.Cout_pad + n_idx * a.n_tile;
-          for (int kb = 0; kb < a.kblocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-            uint8_t* sb = sa + kABytes;
-            mbar_expect_tx(&full_bar[stage], kABytes + b_bytes);
-            tma_load_5d(sa, &tmA, &full_bar[stage], kb * kBlockK, cw, ch, ct, b);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, brow);
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        if (a.mode == 0) {
+          for (int tap = 0; tap < a.ntaps; ++tap) {
+            const int cw = w0 + a.tap_dw[tap];
+            const int ch = h0 + a.tap_dh[tap];
+            const int ct = t0 + a.tap_dt[tap];
+            const int brow = tap * a.Cout_pad + n_idx * a.n_tile;
+            for (int kb = 0; kb < a.kblocks; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+              uint8_t* sb = sa + a.a_bytes;
+              mbar_expect_tx(&full_bar[stage], a.a_bytes + b_bytes);
+              tma_load_5d(sa, &tmA, &full_bar[stage], kb * kBlockK, cw, ch, ct, b);
+              tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, brow);
+              if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
+          for (int dti = 0; dti < a.ntd; ++dti) {
+            const int ct = t0 + dti - a.ntd / 2;
+            for (int dwi = 0; dwi < 3; ++dwi) {
+              for (int kb = 0; kb < a.kblocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+                mbar_expect_tx(&full_bar[stage], a.a_bytes + (resident ? 0u : 3u * b_bytes));
+                // 16 x 10 halo slab: rows h0-1 .. h0+8 at column shift dw
+                tma_load_5d(sa, &tmA, &full_bar[stage], kb * kBlockK, w0 + dwi - 1, h0 - 1, ct, b);
+                if (!resident) {
+                  for (int dhi = 0; dhi < 3; ++dhi) {
+                    const int tap = (dti * 3 + dhi) * 3 + dwi;
+                    tma_load_2d(sa + a.a_bytes + dhi * b_bytes, &tmB, &full_bar[stage], kb * kBlockK,
+                                tap * a.Cout_pad + n_idx * a.n_tile);
+                  }
+                }
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+              }
+            }
           }
         }
       }
@@ -207,8 +366,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t idesc = umma_idesc_f16(kBlockM, static_cast<uint32_t>(a.n_tile), a.fmt);
     int stage = 0;
     uint32_t phase = 0;
-    int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    if (resident) {
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t sw = smem_u32(smem_w);
+    for (int local = 0; local < my_tiles; ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -219,14 +382,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t sb = sa + kABytes;
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sb);
+          if (a.mode == 0) {
+            const uint64_t da = umma_desc_sw128(sa);
+            const uint64_t db = umma_desc_sw128(sa + a.a_bytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // +32 B per K step inside the 128 B swizzle row (encoded >> 4)
-            umma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                     idesc, (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // +32 B per K step inside the 128 B swizzle row (encoded >> 4)
+              umma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                       idesc, (it | k) != 0 ? 1u : 0u);
+            }
+          } else {
+            // it = (dti*3 + dwi)*kblocks + kb
+            const int kb = it % a.kblocks;
+            const int dwi = (it / a.kblocks) % 3;
+            const int dti = it / (3 * a.kblocks);
+#pragma unroll
+            for (int dhi = 0; dhi < 3; ++dhi) {
+              const uint64_t da = umma_desc_sw128(sa + static_cast<uint32_t>(dhi) * 2048u);  // 16 rows x 128 B
+              const int tap = (dti * 3 + dhi) * 3 + dwi;
+              const uint32_t bad = resident ? sw + static_cast<uint32_t>(tap * a.kblocks + kb) * b_bytes
+                                            : sa + a.a_bytes + static_cast<uint32_t>(dhi) * b_bytes;
+              const uint64_t db = umma_desc_sw128(bad);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                         (it | dhi | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
@@ -236,102 +417,55 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    // ===================== epilogue (warps 2..9) =====================
+    const int ewarp = warp - 2;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may read
+    const int half = ewarp >> 2;           // which half of the accumulator columns
     const int row = quarter * 32 + lane;
     const int bw = 1 << a.lbw, bh = 1 << a.lbh;
-    int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    const int col_split = ((a.n_tile / 2 + 15) / 16) * 16;
+    const int col_begin = half ? col_split : 0;
+    const int col_end = half ? a.n_tile : col_split;
+    const int etid = threadIdx.x - 64;     // 0..255
+    // epilogue kind: 0 = fp16 NHWC, 1 = bf16 NHWC, 2 = fp32 NHWC, 3 = fp32 NCHW
+    const int kind = (a.out_layout == FLAIR_OUT_NCHW) ? 3 : (a.out_dtype == FLAIR_F32 ? 2 : (a.out_dtype == FLAIR_F16 ? 0 : 1));
+    for (int local = 0; local < my_tiles; ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int n_idx = tile % a.n_tiles;
-      int m_idx = tile / a.n_tiles;
+      int m_idx, n_idx;
+      tile_at(local, m_idx, n_idx);
       const int tw = m_idx % a.tiles_w; m_idx /= a.tiles_w;
       const int th = m_idx % a.tiles_h; m_idx /= a.tiles_h;
       const int tt = m_idx % a.tiles_t;
       const int b = m_idx / a.tiles_t;
-      const int w = (tw << a.lbw) + (row & (bw - 1));
-      const int h = (th << a.lbh) + ((row >> a.lbw) & (bh - 1));
+      EpiPos pos;
+      pos.w = (tw << a.lbw) + (row & (bw - 1));
+      pos.h = (th << a.lbh) + ((row >> a.lbw) & (bh - 1));
       const int t = (tt << a.lbt) + (row >> (a.lbw + a.lbh));
-      const bool valid = (w < a.Wo) && (h < a.Ho) && (t < a.T);
-      const long long frame = static_cast<long long>(b) * a.T + t;
-      const long long pix = (frame * a.Ho + h) * a.Wo + w;
-      const int n0 = n_idx * a.n_tile;
+      pos.valid = (pos.w < a.Wo) && (pos.h < a.Ho) && (t < a.T);
+      pos.frame = static_cast<long long>(b) * a.T + t;
+      pos.pix = (pos.frame * a.Ho + pos.h) * a.Wo + pos.w;
+      pos.n0 = n_idx * a.n_tile;
+      // bias slice of this N tile -> shared (double-buffered with the accumulator); zero beyond Cout
+      float* sb = s_bias[acc];
+      if (etid < a.n_tile) {
+        const int n = pos.n0 + etid;
+        sb[etid] = (a.bias != nullptr && n < a.Cout) ? __ldg(a.bias + n) : 0.0f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * a.acc_cols) +
                               (static_cast<uint32_t>(quarter * 32) << 16);
-      for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
-        uint32_t r[16];
-        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after divergent stores
-        tmem_ld16(t_addr + static_cast<uint32_t>(c0), r);
-        tmem_ld_wait();
-        const int n = n0 + c0;
-        if (n >= a.Cout) continue;  // warp-uniform: padded columns
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        if (a.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n + j < a.Cout) v[j] += __ldg(a.bias + n + j);
-        }
-        if (a.rowbias != nullptr && valid) {
-          const float* rb = a.rowbias + frame * a.rowbias_stride + n;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n + j < a.Cout) v[j] += __ldg(rb + j);
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], a.act) * a.out_scale;
-
-        const bool full16 = (n + 16 <= a.Cout);
-        if (a.residual != nullptr && valid)
-          add_residual(v, a.residual, a.residual_dtype, pix * a.residual_cstride + n, full16, a.Cout - n);
-        if (a.residual2 != nullptr && valid)
-          add_residual(v, a.residual2, a.residual2_dtype, pix * a.residual2_cstride + n, full16, a.Cout - n);
-        if (!valid) continue;
-        if (a.out_layout == FLAIR_OUT_NCHW) {
-          // fp32 planar output: (frame, n, h, w); lanes walk w -> coalesced per channel
-          float* op = static_cast<float*>(a.out);
-          const long long plane = static_cast<long long>(a.Ho) * a.Wo;
-          for (int j = 0; j < 16; ++j) {
-            if (n + j < a.Cout)
-              op[(frame * a.Cout + n + j) * plane + static_cast<long long>(h) * a.Wo + w] = v[j];
-          }
-        } else if (a.out_dtype == FLAIR_F32) {
-          float* op = static_cast<float*>(a.out) + pix * a.out_cstride + n;
-          if (full16) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              reinterpret_cast<float4*>(op)[q] =
-                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          } else {
-            for (int j = 0; j < 16; ++j)
-              if (n + j < a.Cout) op[j] = v[j];
-          }
-        } else {
-          uint16_t* op = static_cast<uint16_t*>(a.out) + pix * a.out_cstride + n;
-          if (full16) {
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              uint4 u;
-              u.x = pack16(v[8 * q + 0], v[8 * q + 1], a.out_dtype);
-              u.y = pack16(v[8 * q + 2], v[8 * q + 3], a.out_dtype);
-              u.z = pack16(v[8 * q + 4], v[8 * q + 5], a.out_dtype);
-              u.w = pack16(v[8 * q + 6], v[8 * q + 7], a.out_dtype);
-              reinterpret_cast<uint4*>(op)[q] = u;
-            }
-          } else {
-            for (int j = 0; j < 16; ++j) {
-              if (n + j < a.Cout) {
-                const uint32_t u = pack16(v[j], 0.0f, a.out_dtype);
-                op[j] = static_cast<uint16_t>(u & 0xFFFFu);
-              }
-            }
-          }
-        }
+      switch (kind * 4 + a.act) {
+#define EPI_CASE(K, A) case (K) * 4 + (A): epilogue_cols<K, A>(a, t_addr, col_begin, col_end, pos, sb); break;
+        EPI_CASE(0, 0) EPI_CASE(0, 1) EPI_CASE(0, 2) EPI_CASE(0, 3)
+        EPI_CASE(1, 0) EPI_CASE(1, 1) EPI_CASE(1, 2) EPI_CASE(1, 3)
+        EPI_CASE(2, 0) EPI_CASE(2, 1) EPI_CASE(2, 2) EPI_CASE(2, 3)
+        EPI_CASE(3, 0) EPI_CASE(3, 1) EPI_CASE(3, 2) EPI_CASE(3, 3)
+#undef EPI_CASE
+        default: break;
       }
       // this warp is done reading the accumulator buffer
       tc_fence_before();
@@ -346,6 +480,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(a.tmem_cols));
   }
+}
+
+// FLAIR_CONV_MODE = 0 | 1 | 2 forces the tiling mode ceiling (debug / A-B measurements); default: auto
+int flair_conv_mode_override() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("FLAIR_CONV_MODE");
+    v = e ? atoi(e) : -1;
+  }
+  return v;
 }
 
 int ilog2(int v) {
@@ -394,17 +538,35 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
 
   ConvKArgs a{};
   a.B = p->B; a.T = p->T; a.Ho = Ho; a.Wo = Wo;
-  // tile box: as wide as possible, then tall, then across frames
+  // mode selection (see ConvKArgs): halo tiles need a 3x3 spatial kernel, stride 1, and >= 16x8 maps
+  const int env_mode = flair_conv_mode_override();
+  int mode = 0;
+  if (p->kh == 3 && p->kw == 3 && s == 1 && Wo >= 16 && Ho >= 8 && env_mode != 0) mode = 1;
+  // tile box: (mode 0) as wide as possible, then tall, then across frames; (halo) 16 x 8 in one frame
   int bw = pow2_ceil(Wo); if (bw > kBlockM) bw = kBlockM;
   int bh = pow2_ceil(Ho); if (bh > kBlockM / bw) bh = kBlockM / bw;
   int bt = kBlockM / (bw * bh);
+  if (mode != 0) { bw = 16; bh = 8; bt = 1; }
   a.lbw = ilog2(bw); a.lbh = ilog2(bh); a.lbt = ilog2(bt);
   a.tiles_w = ceil_div(Wo, bw); a.tiles_h = ceil_div(Ho, bh); a.tiles_t = ceil_div(p->T, bt);
   a.m_tiles = a.tiles_w * a.tiles_h * a.tiles_t * p->B;
   int n_tile = Cout_pad;
-  if (n_tile > 256) {
-    n_tile = 256;
+  const int n_cap = (mode != 0) ? 144 : 256;  // halo stages carry three weight slabs (>= 3 stages must fit)
+  if (n_tile > n_cap) {
+    n_tile = n_cap;
     while (Cout_pad % n_tile != 0) n_tile -= 16;
+  }
+  const int ntaps_total = p->kt * p->kh * p->kw;
+  const int kblocks_ = Cin_pad / kBlockK;
+  if (mode == 1 && env_mode != 1) {
+    // resident weights: all slabs of one N tile (try the whole Cout first, then 64 columns) + >= 3 A stages
+    const int budget = 227 * 1024 - 1024 - 256 - 2048 - 3 * 20480;
+    int cand[2] = {n_tile, 64};
+    for (int ci = 0; ci < 2; ++ci) {
+      const int nt_ = cand[ci];
+      if (nt_ > n_tile || Cout_pad % nt_ != 0) continue;
+      if (static_cast<long long>(ntaps_total) * kblocks_ * nt_ * 128 <= budget) { mode = 2; n_tile = nt_; break; }
+    }
   }
   a.n_tile = n_tile;
   a.n_tiles = Cout_pad / n_tile;
@@ -434,14 +596,21 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   a.fmt = (p->in_dtype == FLAIR_BF16) ? 1u : 0u;
   a.gn_partial = nullptr; a.gn_groups = 0;
 
-  const uint32_t b_bytes = static_cast<uint32_t>(n_tile) * kBlockK * 2;
-  const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
-  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  const uint32_t b_bytes = static_cast<uint32_t>(n_tile) * kBlockK * 2;  // multiple of 2 KB (n_tile % 16 == 0)
+  a.mode = mode;
+  a.ntd = p->kt;
+  a.b_bytes = b_bytes;
+  a.a_bytes = (mode == 0) ? kABytes : 160u * 128u;  // 16 x 10 halo rows of 128 B
+  a.w_bytes = (mode == 2) ? static_cast<uint32_t>(ntaps_total) * a.kblocks * b_bytes : 0u;
+  uint32_t stage_bytes = a.a_bytes + ((mode == 0) ? b_bytes : (mode == 1 ? 3u * b_bytes : 0u));
+  stage_bytes = (stage_bytes + 1023u) & ~1023u;
+  a.stage_bytes = stage_bytes;
+  const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - 2048 /*static bias*/ - static_cast<int>(a.w_bytes);
   int stages = smem_budget / static_cast<int>(stage_bytes);
   if (stages > 8) stages = 8;
   FLAIR_REQUIRE(stages >= 2, "flair_conv_igemm: tile does not fit shared memory");
   a.stages = stages;
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  const size_t smem_bytes = a.w_bytes + static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
 
   flair_tmap_encode_fn encode = flair_get_tmap_encode();
   FLAIR_REQUIRE(encode != nullptr, "flair_conv_igemm: cuTensorMapEncodeTiled unavailable");
@@ -456,7 +625,7 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
     const cuuint64_t px = static_cast<cuuint64_t>(p->x_cstride) * 2;
     cuuint64_t strides[4] = {px, px * p->W, px * p->W * p->H, px * p->W * p->H * p->T};
     cuuint32_t box[5] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(bw * s),
-                         static_cast<cuuint32_t>(bh * s), static_cast<cuuint32_t>(bt), 1u};
+                         static_cast<cuuint32_t>((mode != 0 ? bh + 2 : bh) * s), static_cast<cuuint32_t>(bt), 1u};
     if (s == 2) { box[1] -= 1; box[2] -= 1; }  // ceil(box/stride) == bw, no overreach
     cuuint32_t estr[5] = {1u, static_cast<cuuint32_t>(s), static_cast<cuuint32_t>(s), 1u, 1u};
     CUresult r = encode(&tmA, dt16, 5, const_cast<void*>(p->x), dims, strides, box, estr,
@@ -481,12 +650,16 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   static bool attr_set = false;
   if (!attr_set) {
     FLAIR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     attr_set = true;
   }
   const int total_tiles = a.m_tiles * a.n_tiles;
   int grid = flair_num_sms();
   if (grid > total_tiles) grid = total_tiles;
+  if (mode == 2) {  // every CTA keeps one N tile: grid must be a multiple of n_tiles
+    grid = (grid / a.n_tiles) * a.n_tiles;
+    if (grid < a.n_tiles) grid = a.n_tiles;
+  }
   conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, a);
   FLAIR_CHECK_LAUNCH();
   return 0;

@@ -13,7 +13,8 @@ L.check(L.lib().flair_check_device(0))
 def run(B, T, H, W, cin, cout, ks, dtype=torch.bfloat16, residual=False, act=L.ACT_NONE, bias=True,
         nchw=False, stride=1, time_it=False, tag=""):
     kt, kh, kw = ks
-    x = torch.randn(B, T, H, W, cin, device=dev).to(dtype)
+    cs = (cin + 7) // 8 * 8
+    x = torch.randn(B, T, H, W, cs, device=dev).to(dtype)[..., :cin]
     w = (torch.randn(cout, cin, kt, kh, kw, device=dev) / (cin * kt * kh * kw) ** 0.5)
     b = torch.randn(cout, device=dev) if bias else None
     wpk = ops.pack_conv_weight(w, dtype)
@@ -66,6 +67,10 @@ cases = [
     dict(B=1, T=3, H=16, W=16, cin=64, cout=64, ks=(3, 1, 1), tag="t311"),
     dict(B=1, T=2, H=32, W=32, cin=64, cout=128, ks=(1, 3, 3), dtype=torch.float16, tag="fp16"),
     dict(B=1, T=2, H=32, W=32, cin=64, cout=128, ks=(1, 3, 3), stride=2, tag="stride2"),
+    dict(B=1, T=3, H=24, W=40, cin=64, cout=64, ks=(1, 3, 3), residual=True, tag="ragged-24x40"),
+    dict(B=2, T=3, H=32, W=16, cin=128, cout=256, ks=(3, 3, 3), tag="3d-halo-b2"),
+    dict(B=1, T=10, H=16, W=16, cin=192, cout=64, ks=(1, 3, 3), act=L.ACT_RELU, tag="192->64"),
+    dict(B=1, T=4, H=64, W=64, cin=128, cout=128, ks=(1, 3, 3), tag="128-resident"),
 ]
 for c in cases:
     try:
