@@ -138,62 +138,114 @@ planes_to_cl_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, i
 // (first C from xa, last C from xb).  om: [N][H][W][om_cstride] 16-bit raw offset-net output with
 // channel blocks o1 (dg/2*18) | o2 (dg/2*18) | mask (dg*9)  (th.chunk(out, 3), unet_new.py:877).
 // cols: [N*H*W][9 * 2C], column = tap*2C + ci.
+//
+// One CTA = kDefPix pixels.  Phase 1 stages the raw offset rows through shared memory with 16-byte
+// loads and turns them into (dy, dx, mask) once per (pixel, group, tap); phase 2 gathers: consecutive
+// threads write consecutive 16-byte column vectors, the four bilinear corners are 16-byte channel
+// vectors of the channels-last source.
+constexpr int kDefPix = 8;
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(256)
 deform_im2col_kernel(const uint16_t* __restrict__ xa, const uint16_t* __restrict__ xb, int xa_cstride, int xb_cstride,
                      const uint16_t* __restrict__ om, int om_cstride, int om_dtype, const float* __restrict__ flow1,
                      const float* __restrict__ flow2, uint16_t* __restrict__ cols, int N, int H, int W, int C, int dg,
                      float mrm, int dtype) {
-  const int cpg = 2 * C / dg;       // channels per deform group (8 or 16)
-  const int vpg = cpg / 8;          // 16-byte vectors per group
-  const int half_g = dg / 2;
+  extern __shared__ float dsm[];  // [kDefPix][3][dg*9]: dy | dx | mask
+  const int pairs = dg * 9;
+  const int nch = pairs * 3;  // channels of the offset-net output actually used
   const long long hw = static_cast<long long>(H) * W;
-  const long long items = static_cast<long long>(N) * hw * 9 * dg * vpg;
-  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
-       it += static_cast<long long>(gridDim.x) * blockDim.x) {
-    long long r = it;
-    const int vi = static_cast<int>(r % vpg); r /= vpg;
-    const int g = static_cast<int>(r % dg); r /= dg;
-    const int tap = static_cast<int>(r % 9); r /= 9;
-    const long long pix = r;
+  const long long total_pix = static_cast<long long>(N) * hw;
+  const long long pix0 = static_cast<long long>(blockIdx.x) * kDefPix;
+  const int half_g = dg / 2;
+  // ---- phase 1a: raw values -> smem (as fp32), 8 channels per 16-byte load
+  const int vec_per_pix = nch / 8;
+  for (int i = threadIdx.x; i < kDefPix * vec_per_pix; i += blockDim.x) {
+    const int p = i / vec_per_pix, v = i % vec_per_pix;
+    if (pix0 + p >= total_pix) continue;
+    float f[8];
+    ld8(om + (pix0 + p) * om_cstride + v * 8, om_dtype, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dsm[p * nch + v * 8 + j] = f[j];
+  }
+  __syncthreads();
+  // ---- phase 1b: (dy, dx, mask) per (pixel, group, tap), in place: reads raw[oc], raw[oc+1], raw[2*pairs+pair]
+  float dyv[5], dxv[5], mkv[5];  // kDefPix*pairs / 256 <= 5 (checked on the host)
+#pragma unroll
+  for (int cnt = 0; cnt < 5; ++cnt) {
+    const int i = threadIdx.x + cnt * 256;
+    const int p = i / pairs, pair = i % pairs;  // pair = g*9 + tap
+    const long long pix = pix0 + p;
+    float dy = 0.f, dx = 0.f, mk = 0.f;
+    if (i < kDefPix * pairs && pix < total_pix) {
+      const int g = pair / 9;
+      const long long n = pix / hw, off = pix - n * hw;
+      const float* fl = (g >= half_g) ? flow2 : flow1;
+      const float* raw = dsm + p * nch;
+      // offset channel (g*9 + tap)*2 + {0: dy, 1: dx} inside cat(o1, o2); flow.flip(1) = (fy, fx)
+      dy = mrm * tanh_fast(raw[pair * 2]) + __ldg(fl + (n * 2 + 1) * hw + off);
+      dx = mrm * tanh_fast(raw[pair * 2 + 1]) + __ldg(fl + (n * 2 + 0) * hw + off);
+      mk = 1.0f / (1.0f + __expf(-raw[2 * pairs + pair]));
+    }
+    dyv[cnt] = dy; dxv[cnt] = dx; mkv[cnt] = mk;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int cnt = 0; cnt < 5; ++cnt) {
+    const int i = threadIdx.x + cnt * 256;
+    if (i < kDefPix * pairs) {
+      const int p = i / pairs, pair = i % pairs;
+      dsm[p * nch + pair] = dyv[cnt];
+      dsm[p * nch + pairs + pair] = dxv[cnt];
+      dsm[p * nch + 2 * pairs + pair] = mkv[cnt];
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: gather.  item = ((p*9 + tap)*dg + g)*vpg + vi  -> consecutive 16-byte outputs
+  const int cpg = 2 * C / dg, vpg = cpg / 8;
+  const int items = kDefPix * 9 * dg * vpg;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    int r = it;
+    const int vi = r % vpg; r /= vpg;
+    const int g = r % dg; r /= dg;
+    const int tap = r % 9;
+    const int p = r / 9;
+    const long long pix = pix0 + p;
+    if (pix >= total_pix) continue;
     const long long n = pix / hw, off = pix - n * hw;
     const int h = static_cast<int>(off / W), w = static_cast<int>(off % W);
-    const uint16_t* orow = om + pix * om_cstride;
-    auto rd = [&](int ch) -> float {
-      const uint16_t b = __ldg(orow + ch);
-      if (om_dtype == FLAIR_F16) return __half2float(*reinterpret_cast<const __half*>(&b));
-      return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&b));
-    };
-    // offset channel (g*9 + tap)*2 + {0: dy, 1: dx} inside cat(o1, o2); flow.flip(1) = (fy, fx)
-    const int oc = (g * 9 + tap) * 2;
-    const bool second = g >= half_g;
-    const float* fl = second ? flow2 : flow1;
-    const float dy = mrm * tanhf(rd(oc)) + __ldg(fl + (n * 2 + 1) * hw + off);
-    const float dx = mrm * tanhf(rd(oc + 1)) + __ldg(fl + (n * 2 + 0) * hw + off);
-    const float mk = 1.0f / (1.0f + __expf(-rd(dg * 18 + g * 9 + tap)));
-    const float sy = h + tap / 3 - 1 + dy, sx = w + tap % 3 - 1 + dx;
+    const int pair = g * 9 + tap;
+    const float sy = h + tap / 3 - 1 + dsm[p * nch + pair];
+    const float sx = w + tap % 3 - 1 + dsm[p * nch + pairs + pair];
+    const float mk = dsm[p * nch + 2 * pairs + pair];
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (sy > -1.f && sy < H && sx > -1.f && sx < W) {  // torchvision bilinear_interpolate bounds
       const float fy0 = floorf(sy), fx0 = floorf(sx);
       const int y0 = static_cast<int>(fy0), x0 = static_cast<int>(fx0);
       const float ay = sy - fy0, ax = sx - fx0;
+      const bool second = g >= half_g;
       const int cg = g * cpg + vi * 8;  // channel inside the 2C concat
       const uint16_t* src = second ? xb : xa;
       const int cs = second ? xb_cstride : xa_cstride;
       const int cl = second ? cg - C : cg;
+      const uint16_t* base = src + n * hw * cs + cl;
 #pragma unroll
       for (int yy = 0; yy < 2; ++yy)
 #pragma unroll
         for (int xx = 0; xx < 2; ++xx) {
           const int py = y0 + yy, px = x0 + xx;
           if (py < 0 || py > H - 1 || px < 0 || px > W - 1) continue;
-          const float wgt = (yy ? ay : 1.f - ay) * (xx ? ax : 1.f - ax);
+          const float wgt = (yy ? ay : 1.f - ay) * (xx ? ax : 1.f - ax) * mk;
           float v[8];
-          ld8(src + (n * hw + static_cast<long long>(py) * W + px) * cs + cl, dtype, v);
+          ld8(base + (static_cast<long long>(py) * W + px) * cs, dtype, v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, v[j], acc[j]);
         }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] *= mk;
     }
     st8(cols + pix * (18LL * C) + static_cast<long long>(tap) * 2 * C + g * cpg + vi * 8, dtype, acc);
   }
@@ -267,8 +319,11 @@ extern "C" int flair_deform_im2col(const void* xa, const void* xb, int xa_cstrid
   FLAIR_REQUIRE(deform_groups > 0 && deform_groups % 2 == 0 && (2 * C) % deform_groups == 0 &&
                     ((2 * C) / deform_groups) % 8 == 0,
                 "flair_deform_im2col: channels per deform group must be a multiple of 8 (C=%d, dg=%d)", C, deform_groups);
-  const long long items = static_cast<long long>(N) * H * W * 9 * deform_groups * ((2 * C / deform_groups) / 8);
-  deform_im2col_kernel<<<blocks_for(items), 256, 0, stream>>>(
+  FLAIR_REQUIRE((deform_groups * 27) % 8 == 0 && deform_groups * 9 * kDefPix <= 5 * 256 && om_cstride % 8 == 0,
+                "flair_deform_im2col: unsupported deform_groups=%d", deform_groups);
+  const long long total_pix = static_cast<long long>(N) * H * W;
+  const size_t smem = sizeof(float) * kDefPix * deform_groups * 27;
+  deform_im2col_kernel<<<static_cast<unsigned>(ceil_div_ll(total_pix, kDefPix)), 256, smem, stream>>>(
       static_cast<const uint16_t*>(xa), static_cast<const uint16_t*>(xb), xa_cstride, xb_cstride,
       static_cast<const uint16_t*>(om), om_cstride, om_dtype, flow1, flow2, static_cast<uint16_t*>(cols), N, H, W, C,
       deform_groups, max_residue_magnitude, dtype);

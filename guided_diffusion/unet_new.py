@@ -450,82 +450,76 @@ class BasicVSRPP(nn.Module, _Packed):
         if hidden.shape[0] > 1:  # windows are independent: run them one by one (the demo uses B = 1)
             outs = []
             for b in range(hidden.shape[0]):
-                ff, fb = ctx.flows[hidden.shape[3]]
                 w = ctx.weights
-                sub = _Ctx(ctx.emb_all, {hidden.shape[3]: (ff[b:b + 1], fb[b:b + 1])},
-                           w[b:b + 1] if th.is_tensor(w) else w, ctx.cross, ctx.dtype, ctx.T)
+                sub = _Ctx(ctx.emb_all, {hidden.shape[3]: tuple(f[b:b + 1] for f in ctx.flows[hidden.shape[3]])},
+                           w[b:b + 1] if th.is_tensor(w) else w, ctx.cross, ctx.dtype, ctx.T, ctx.sdtype)
                 outs.append(self.forward(hidden[b:b + 1], sub))
             return th.cat(outs, 0)
-        stream = hidden              # residual-stream copy (may be fp32): only the final add reads it
+        stream = hidden               # residual-stream copy (may be fp32): only the final add reads it
         hidden = ctx.operand(hidden)  # 16-bit operand copy: features / warps / convs
-        B, T, H, W, C = hidden.shape
+        _, T, H, W, C = hidden.shape
         dt, dev = hidden.dtype, hidden.device
-        flows_forward, flows_backward = ctx.flows[W]
+        f12 = {"backward_1": ctx.flows[W][3][0], "forward_1": ctx.flows[W][2][0]}  # [T,4,H,W]: f1 | composed f2
         weight = ctx.weights
         wmap = None
         if weight is not None and not isinstance(weight, float):
             if weight.shape[-2] != H or weight.shape[-1] != W:
-                weight = F.interpolate(weight.flatten(0, 1), size=(H, W), mode="nearest").unflatten(0, (B, T))
-            wmap = weight.reshape(B, T, H, W).float().contiguous()
+                weight = F.interpolate(weight.flatten(0, 1), size=(H, W), mode="nearest").unflatten(0, (1, T))
+            wmap = weight.reshape(T, H, W).float().contiguous()
         elif isinstance(weight, float) and weight != 1.0:
-            wmap = th.full((B, T, H, W), weight, dtype=th.float32, device=dev)
+            wmap = th.full((T, H, W), weight, dtype=th.float32, device=dev)
+        frames = hidden[0]  # [T,H,W,C]
         cpad = (3 * C + 4 + 7) // 8 * 8
-        feats = {}
+        # reconstruction input for ALL frames: [spatial | backward feature | forward feature]; the two
+        # propagation passes write their outputs straight into its channel slices
+        rec_cat = th.empty(1, T, H, W, 3 * C, dtype=dt, device=dev)
+        ops.copy_channels_into(frames[None], rec_cat, 0)
         for name in ("backward_1", "forward_1"):
-            n_other = 1 if name == "forward_1" else 0
-            flows = flows_backward if "backward" in name else flows_forward
-            order = list(range(T))
-            flow_idx = list(range(-1, T - 1))
-            if "backward" in name:
-                order = order[::-1]
-                flow_idx = order
-            store = [None] * T
+            fwd = name == "forward_1"
+            so = 2 * C if fwd else C
+            order = list(range(T)) if fwd else list(range(T - 1, -1, -1))
+            # per-frame inputs that do not depend on the recurrence, written once for all frames
+            cond_all = th.empty(1, T, H, W, cpad, dtype=dt, device=dev)     # [warp(prop) | cur | warp(prev2) | f1 f2]
+            ops.copy_channels_into(frames[None], cond_all, C)
+            ops.planes_to_cl(f12[name], cond_all[0], 3 * C)
+            cat_all = th.empty(1, T, H, W, (3 if fwd else 2) * C, dtype=dt, device=dev)  # [cur | (backward) | aligned]
+            ops.copy_channels_into(frames[None], cat_all, 0)
+            if fwd:
+                ops.copy_channels_into(rec_cat[..., C:2 * C], cat_all, C)
+            ao = (2 if fwd else 1) * C
             prop = prev2 = None
             for i, idx in enumerate(order):
-                cur = hidden[:, idx]  # [B,H,W,C] view
-                # [cur | other branches | prop] concat buffer for the backbone
-                cat = th.empty(1, B, H, W, (2 + n_other) * C, dtype=dt, device=dev)
-                ops.copy_channels_into(cur[None], cat, 0)
-                if n_other:
-                    ops.copy_channels_into(feats["backward_1"][idx][None], cat, C)
-                prop_slot = cat[0, ..., (1 + n_other) * C:]
+                aligned = cat_all[0, idx:idx + 1, :, :, ao:ao + C]  # [1,H,W,C] slice: deform output / zeros
                 if i == 0:
-                    prop_slot.zero_()
+                    aligned.zero_()
                 else:
-                    f1 = flows[:, flow_idx[i]].contiguous()
-                    cond = th.empty(1, B, H, W, cpad, dtype=dt, device=dev)
-                    ops.flow_warp(prop, f1, out=cond[0, ..., :C])
-                    ops.copy_channels_into(cur[None], cond, C)
+                    cond = cond_all[0, idx:idx + 1]
+                    f1, f2 = f12[name][idx:idx + 1, 0:2], f12[name][idx:idx + 1, 2:4]
+                    ops.flow_warp(prop, f1, out=cond[..., :C])
                     if i > 1:
-                        f2 = ops.flow_compose(flows[:, flow_idx[i - 1]].contiguous(), f1)
-                        ops.flow_warp(prev2, f2, out=cond[0, ..., 2 * C:3 * C])
+                        ops.flow_warp(prev2, f2, out=cond[..., 2 * C:3 * C])
                         xb = prev2
                     else:
-                        f2 = th.zeros_like(f1)
-                        cond[0, ..., 2 * C:3 * C].zero_()
-                        xb = th.zeros_like(prop)
-                    ops.planes_to_cl(f1, cond[0], 3 * C)
-                    ops.planes_to_cl(f2, cond[0], 3 * C + 2)
-                    self.deform_align[name].run(prop, xb, cond[..., : 3 * C + 4], f1, f2, ctx.dtype,
-                                                out=prop_slot[None])
-                new = th.empty(1, B, H, W, C, dtype=dt, device=dev)
-                self.backbone[name].run(cat, ctx.dtype, extra_residual=prop_slot[None], out=new)
-                new = new[0]
+                        cond[..., 2 * C:3 * C].zero_()
+                        xb = self._zeros(prop)
+                    self.deform_align[name].run(prop, xb, cond[None, ..., : 3 * C + 4], f1, f2, ctx.dtype,
+                                                out=aligned[None])
+                new = rec_cat[0, idx:idx + 1, :, :, so:so + C]
+                self.backbone[name].run(cat_all[:, idx:idx + 1], ctx.dtype, extra_residual=aligned[None], out=new[None])
                 if wmap is not None:
-                    ops.scale_pixels_(new, wmap[:, idx].contiguous())
+                    ops.scale_pixels_(new, wmap[idx:idx + 1])
                 prev2, prop = prop, new
-                store[idx] = new
-            feats[name] = store
-        out = th.empty_like(stream)
+        # reconstruction + zero-init 1x1 + residual: not recurrent -> one batched launch chain for all frames
         pk_last = self.packed(ctx.dtype)
-        for i in range(T):
-            cat = th.empty(1, B, H, W, 3 * C, dtype=dt, device=dev)
-            ops.copy_channels_into(hidden[:, i][None], cat, 0)
-            ops.copy_channels_into(feats["backward_1"][i][None], cat, C)
-            ops.copy_channels_into(feats["forward_1"][i][None], cat, 2 * C)
-            rec = self.reconstruction.run(cat, ctx.dtype)
-            ops.conv(rec, pk_last[0], C, (1, 1, 1), bias=pk_last[1], residual=stream[:, i][None], out=out[:, i][None])
-        return out
+        rec = self.reconstruction.run(rec_cat, ctx.dtype)
+        return ops.conv(rec, pk_last[0], C, (1, 1, 1), bias=pk_last[1], residual=stream, out_dtype=stream.dtype)
+
+    def _zeros(self, like):
+        z = getattr(self, "_zero_buf", None)
+        if z is None or z.shape != like.shape or z.dtype != like.dtype or z.device != like.device:
+            z = th.zeros(like.shape, dtype=like.dtype, device=like.device)
+            self._zero_buf = z
+        return z
 
 
 # --------------------------------------------------------------------------------------------------
@@ -751,6 +745,24 @@ class UNetModel(nn.Module):
         b = lqs[:, 1:].reshape(-1, c, h, w)
         return self.spynet(b, a).view(n, t - 1, 2, h, w), self.spynet(a, b).view(n, t - 1, 2, h, w)
 
+    @staticmethod
+    def _flow_pack(flows, forward):
+        """[B,T,4,H,W] per propagation direction, indexed by frame: channels 0:2 = the flow that aligns the
+        previous feature to this frame (f1, unet_new.py:704), 2:4 = the composed second-order flow
+        f1 + warp(f2, f1) (:716-718).  Depends on the flows only -> computed once per window."""
+        B, tm1, _, H, W = flows.shape
+        T = tm1 + 1
+        out = th.zeros(B, T, 4, H, W, dtype=th.float32, device=flows.device)
+        order = list(range(T)) if forward else list(range(T - 1, -1, -1))
+        flow_idx = list(range(-1, T - 1)) if forward else order
+        for i, idx in enumerate(order):
+            if i > 0:
+                f1 = flows[:, flow_idx[i]].contiguous()
+                out[:, idx, 0:2] = f1
+                if i > 1:
+                    out[:, idx, 2:4] = ops.flow_compose(flows[:, flow_idx[i - 1]].contiguous(), f1)
+        return out
+
     def _flows(self, rnn_input, num_frames):
         key = (rnn_input.data_ptr(), tuple(rnn_input.shape), rnn_input._version,
                tuple((p.data_ptr(), p._version) for p in self.spynet.parameters()))
@@ -761,7 +773,8 @@ class UNetModel(nn.Module):
                 if rnn_input.shape[-1] != res:
                     fi = F.interpolate(rnn_input.flatten(0, 1).float(), (res, res), mode="bicubic").unflatten(
                         0, rnn_input.shape[:2])
-                flows[res] = tuple(f.float().contiguous() for f in self.compute_flow(fi.float()))
+                ff, fb = (f.float().contiguous() for f in self.compute_flow(fi.float()))
+                flows[res] = (ff, fb, self._flow_pack(ff, True), self._flow_pack(fb, False))
             self._flow_cache = {"key": key, "flows": flows, "src": rnn_input}
         return self._flow_cache["flows"]
 
