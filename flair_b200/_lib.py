@@ -21,6 +21,7 @@ class ConvParams(C.Structure):
         ("Cin", C.c_int), ("x_cstride", C.c_int), ("wgt", C.c_void_p), ("Cout", C.c_int),
         ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("stride_hw", C.c_int),
         ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_stride", C.c_int),
+        ("rowscale", C.c_void_p), ("rowscale_stride", C.c_int),
         ("residual", C.c_void_p), ("residual_dtype", C.c_int), ("residual_cstride", C.c_int),
         ("residual2", C.c_void_p), ("residual2_dtype", C.c_int), ("residual2_cstride", C.c_int),
         ("out", C.c_void_p), ("out_dtype", C.c_int), ("out_layout", C.c_int),

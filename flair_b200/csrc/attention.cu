@@ -121,9 +121,11 @@ attn_temporal_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ ou
   const int heads = C / kD;
   const int half = frames / 2;
   const long long items = static_cast<long long>(B) * T * P * heads * 8;
-  // grid is sized so that the trip count is uniform per warp (items is a multiple of 32)
-  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
-       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const long long items32 = (items + 31) & ~31LL;  // warp-uniform trip count (shuffles below)
+  for (long long it0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it0 < items32;
+       it0 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const bool live = it0 < items;
+    const long long it = live ? it0 : items - 8 + (it0 & 7);  // idle lanes redo the last octet, store nothing
     const int sub = static_cast<int>(it & 7);
     long long r = it >> 3;
     const int hd = static_cast<int>(r % heads); r /= heads;
@@ -179,7 +181,7 @@ attn_temporal_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ ou
     uint4 u;
     u.x = pk16(o[0], o[1], dtype); u.y = pk16(o[2], o[3], dtype);
     u.z = pk16(o[4], o[5], dtype); u.w = pk16(o[6], o[7], dtype);
-    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * T + t) * P + p) * C + c0) = u;
+    if (live) *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * T + t) * P + p) * C + c0) = u;
   }
 }
 
@@ -207,7 +209,6 @@ extern "C" int flair_attn_temporal(const void* qkv, void* out, const float* cq, 
   FLAIR_REQUIRE(C % kD == 0 && (frames == 5 || frames == 7) && T > 0 && B > 0 && P > 0,
                 "flair_attn_temporal: unsupported C=%d frames=%d", C, frames);
   FLAIR_REQUIRE(dtype == FLAIR_BF16 || dtype == FLAIR_F16, "flair_attn_temporal: 16-bit maps only");
-  FLAIR_REQUIRE((C / kD) % 4 == 0, "flair_attn_temporal: heads must be a multiple of 4 (warp-uniform trip count)");
   const long long items = static_cast<long long>(B) * T * P * (C / kD) * 8;
   long long blocks = ceil_div_ll(items, 256);
   const long long cap = static_cast<long long>(flair_num_sms()) * 8;

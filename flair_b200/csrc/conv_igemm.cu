@@ -58,6 +58,8 @@ struct ConvKArgs {
   const float* bias;
   const float* rowbias;
   int rowbias_stride;
+  const float* rowscale;
+  int rowscale_stride;
   const void* residual;
   int residual_dtype;
   long long residual_cstride;
@@ -189,6 +191,12 @@ __device__ __forceinline__ void epilogue_cols(const ConvKArgs& a, uint32_t t_add
       else if (ACT == FLAIR_ACT_LRELU01) y = y > 0.0f ? y : 0.1f * y;
       else if (ACT == FLAIR_ACT_SILU) y = silu_f(y);
       v[j] = y * a.out_scale;
+    }
+    if (a.rowscale != nullptr && pos.valid) {  // per-(frame, channel) gate, e.g. sigmoid(g) of TemporalWrapper2
+      const float* rs = a.rowscale + pos.frame * a.rowscale_stride + n;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n + j < a.Cout) v[j] *= __ldg(rs + j);
     }
     if (a.residual != nullptr && pos.valid)
       add_residual(v, a.residual, a.residual_dtype, pos.pix * a.residual_cstride + n, full16, a.Cout - n);
@@ -586,6 +594,7 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
       }
   a.ntaps = nt;
   a.bias = p->bias; a.rowbias = p->rowbias; a.rowbias_stride = p->rowbias_stride;
+  a.rowscale = p->rowscale; a.rowscale_stride = p->rowscale_stride;
   a.residual = p->residual; a.residual_dtype = p->residual_dtype;
   a.residual_cstride = p->residual_cstride;
   a.residual2 = p->residual2; a.residual2_dtype = p->residual2_dtype;

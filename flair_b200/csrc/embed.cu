@@ -50,7 +50,8 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ Wt, con
       const float bb = bias ? __ldg(bias + n) : 0.f;
       for (int mm = 0; mm < mb; ++mm) {
         float v = acc[mm] + bb;
-        if (silu_out) v = v / (1.0f + expf(-v));
+        if (silu_out == 1) v = v / (1.0f + expf(-v));
+        else if (silu_out == 2) v = 1.0f / (1.0f + expf(-v));
         y[static_cast<long long>(m0 + mm) * N + n] = v;
       }
     }

@@ -54,7 +54,7 @@ def pack_conv_weight(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
     return out.contiguous()
 
 
-def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, residual=None, residual2=None, out=None,
+def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, rowscale=None, residual=None, residual2=None, out=None,
          out_dtype=None, act=L.ACT_NONE, stride=1, nchw_out=False, out_scale=1.0):
     """Implicit-GEMM convolution (see flair_conv_igemm in include/flair_b200.h).
 
@@ -79,6 +79,8 @@ def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, residual=Non
     p.bias = _ptr(bias)
     p.rowbias = _ptr(rowbias)
     p.rowbias_stride = 0 if rowbias is None else rowbias.stride(0)
+    p.rowscale = _ptr(rowscale)
+    p.rowscale_stride = 0 if rowscale is None else rowscale.stride(0)
     if residual is not None:
         p.residual = _ptr(residual)
         p.residual_dtype = _DT[residual.dtype]
@@ -335,8 +337,9 @@ def timestep_embedding(t, freqs):
     return out
 
 
-def linear_f32(x, Wt, bias=None, silu_in=False, silu_out=False):
+def linear_f32(x, Wt, bias=None, silu_in=False, silu_out=False, sigmoid_out=False):
     """y = act_out(bias + act_in(x) @ Wt), Wt [K,N] fp32 (small M)."""
+    silu_out = 2 if sigmoid_out else int(silu_out)
     M, K = x.shape
     N = Wt.shape[1]
     y = torch.empty(M, N, dtype=torch.float32, device=x.device)

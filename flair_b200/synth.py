@@ -29,6 +29,10 @@ def _gen(seed: int, key: str) -> torch.Generator:
 def synthetic_tensor(key: str, shape, seed: int = 1234) -> torch.Tensor:
     """Variance-preserving random tensor for one state-dict entry."""
     shape = tuple(shape)
+    if "spynet." in key:
+        # sr3 registers ONE shared SPyNet under every BasicVSR++ module (sr3.py:340,382): all copies of a
+        # key must hold the same values, like in a real checkpoint
+        key = key[key.index("spynet."):]
     g = _gen(seed, key)
     leaf = key.rsplit(".", 1)[-1]
     if key.endswith("spynet.mean"):

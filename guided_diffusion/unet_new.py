@@ -45,11 +45,12 @@ from .nn_new import avg_pool_nd, conv_nd, linear, normalization, timestep_embedd
 # --------------------------------------------------------------------------------------------------
 class _Ctx:
     """dtype: GEMM operand type (bf16/fp16); sdtype: storage type of the residual stream."""
-    __slots__ = ("emb_all", "flows", "weights", "cross", "dtype", "T", "sdtype")
+    __slots__ = ("emb_all", "flows", "weights", "cross", "dtype", "T", "sdtype", "emb_plain", "gates")
 
     def __init__(self, emb_all, flows, weights, cross, dtype, T, sdtype=None):
         self.emb_all, self.flows, self.weights, self.cross, self.dtype, self.T = emb_all, flows, weights, cross, dtype, T
         self.sdtype = sdtype or dtype
+        self.emb_plain = self.gates = None  # sr3: un-activated noise embeddings / sigmoid gates
 
     def operand(self, x):
         """A 16-bit GEMM-operand copy of a residual-stream map (no-op when the stream is already 16-bit)."""
@@ -150,8 +151,11 @@ class ResBlock(TimestepBlock, _Packed):
     """GN-SiLU-conv, FiLM'd GN-SiLU-conv, plus skip (reference :198-329); dims=3 -> 3x3x3 convs."""
 
     def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False,
-                 use_scale_shift_norm=False, dims=2, use_checkpoint=False, up=False, down=False):
+                 use_scale_shift_norm=False, dims=2, use_checkpoint=False, up=False, down=False, kernel_size=3,
+                 padding=1):
         super().__init__()
+        k3 = (kernel_size,) * dims if isinstance(kernel_size, int) else tuple(kernel_size)
+        self._ks = (1,) * (3 - len(k3)) + k3  # (kt, kh, kw) as flair_conv_igemm wants it
         self.channels, self.emb_channels, self.dropout = channels, emb_channels, dropout
         self.out_channels = out_channels or channels
         self.use_conv, self.use_checkpoint, self.use_scale_shift_norm = use_conv, use_checkpoint, use_scale_shift_norm
@@ -159,7 +163,7 @@ class ResBlock(TimestepBlock, _Packed):
         wrap = LazyReshaper2D if dims == 2 else LazyReshaper3D
         self.in_layers = nn.Sequential(
             LazyReshaper3D(normalization(channels)), nn.SiLU(),
-            wrap(conv_nd(dims, channels, self.out_channels, 3, padding=1)))
+            wrap(conv_nd(dims, channels, self.out_channels, kernel_size, padding=padding)))
         self.updown = up or down
         self._resample = 1 if up else (2 if down else 0)
         if up:
@@ -174,7 +178,7 @@ class ResBlock(TimestepBlock, _Packed):
             nn.SiLU(), linear(emb_channels, 2 * self.out_channels if use_scale_shift_norm else self.out_channels))
         self.out_layers = nn.Sequential(
             LazyReshaper3D(normalization(self.out_channels)), nn.SiLU(), nn.Dropout(p=dropout),
-            zero_module(wrap(conv_nd(dims, self.out_channels, self.out_channels, 3, padding=1))))
+            zero_module(wrap(conv_nd(dims, self.out_channels, self.out_channels, kernel_size, padding=padding))))
         if self.out_channels == channels:
             self.skip_connection = nn.Identity()
         elif use_conv:
@@ -193,10 +197,12 @@ class ResBlock(TimestepBlock, _Packed):
             pk.update(ws=_w(sc, dtype), bs=_f(sc.bias), ks=tuple(sc.kernel_size))
         return pk
 
-    def forward(self, x, ctx):
+    def forward(self, x, ctx, gate=None):
+        """gate: optional per-(frame, channel) sigmoid gate of sr3.TemporalWrapper2, fused into the last conv:
+        (1-s) x + s (x + branch) == x + s * branch."""
         pk = self.packed(ctx.dtype)
         cout = self.out_channels
-        ks = (1, 3, 3) if self.dims == 2 else (3, 3, 3)
+        ks = self._ks
         off, width = self._emb_slot
         emb = ctx.emb_all[:, off:off + width]
         a1 = ops.gn_apply(x, ops.gn_stats(x), pk["g1"], pk["be1"], silu=True, resample=self._resample,
@@ -215,7 +221,7 @@ class ResBlock(TimestepBlock, _Packed):
             xs = ops.conv(xs, pk["ws"], cout, (1, 1, 1) if kk[-1] == 1 else ks, bias=pk["bs"], out_dtype=ctx.sdtype)
         else:
             xs = ops.gn_apply(x, None, resample=self._resample) if self.updown else x
-        return ops.conv(a2, pk["w2"], cout, ks, bias=pk["b2"], residual=xs, out_dtype=ctx.sdtype)
+        return ops.conv(a2, pk["w2"], cout, ks, bias=pk["b2"], residual=xs, rowscale=gate, out_dtype=ctx.sdtype)
 
 
 class _AttnBase(_Packed):
@@ -322,13 +328,13 @@ class TemporalAttention(nn.Module, _Packed):
             ck=(pe[rest] @ wk.t() + self.k_linear.bias.detach().float()).contiguous(),
             bv=_f(self.v_linear.bias), wp=_w(pj, dtype), bp=_f(pj.bias))
 
-    def forward(self, h, ctx):
+    def forward(self, h, ctx, gate=None):
         pk = self.packed(ctx.dtype)
         c = self.channels
         x = ops.gn_apply(h, ops.gn_stats(h), pk["g"], pk["b"], out_dtype=ctx.dtype)
         qkv = ops.conv(x, pk["wqkv"], 3 * c, (1, 1, 1))
         att = ops.attn_temporal(qkv, pk["cq"], pk["ck"], pk["bv"], self.num_frames)
-        return ops.conv(att, pk["wp"], c, (1, 1, 1), bias=pk["bp"], residual=h, out_dtype=h.dtype)
+        return ops.conv(att, pk["wp"], c, (1, 1, 1), bias=pk["bp"], residual=h, rowscale=gate, out_dtype=h.dtype)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -446,14 +452,15 @@ class BasicVSRPP(nn.Module, _Packed):
         self.reconstruction = ResidualBlocksWithInputConv(3 * mid_channels, mid_channels, 1)
         self.conv_last = zero_module(nn.Conv2d(mid_channels, mid_channels, 1, 1))
 
-    def forward(self, hidden, ctx):
+    def forward(self, hidden, ctx, gate=None):
         if hidden.shape[0] > 1:  # windows are independent: run them one by one (the demo uses B = 1)
             outs = []
+            T_ = hidden.shape[1]
             for b in range(hidden.shape[0]):
                 w = ctx.weights
                 sub = _Ctx(ctx.emb_all, {hidden.shape[3]: tuple(f[b:b + 1] for f in ctx.flows[hidden.shape[3]])},
                            w[b:b + 1] if th.is_tensor(w) else w, ctx.cross, ctx.dtype, ctx.T, ctx.sdtype)
-                outs.append(self.forward(hidden[b:b + 1], sub))
+                outs.append(self.forward(hidden[b:b + 1], sub, None if gate is None else gate[b * T_:(b + 1) * T_]))
             return th.cat(outs, 0)
         stream = hidden               # residual-stream copy (may be fp32): only the final add reads it
         hidden = ctx.operand(hidden)  # 16-bit operand copy: features / warps / convs
@@ -512,7 +519,8 @@ class BasicVSRPP(nn.Module, _Packed):
         # reconstruction + zero-init 1x1 + residual: not recurrent -> one batched launch chain for all frames
         pk_last = self.packed(ctx.dtype)
         rec = self.reconstruction.run(rec_cat, ctx.dtype)
-        return ops.conv(rec, pk_last[0], C, (1, 1, 1), bias=pk_last[1], residual=stream, out_dtype=stream.dtype)
+        return ops.conv(rec, pk_last[0], C, (1, 1, 1), bias=pk_last[1], residual=stream, rowscale=gate,
+                        out_dtype=stream.dtype)
 
     def _zeros(self, like):
         z = getattr(self, "_zero_buf", None)

@@ -59,7 +59,7 @@ int flair_check_device(int dev);
  *
  *   out[b,t,h,w,n] = act( bias[n] + rowbias[b*T+t, n]
  *                         + sum_{taps,c} x[b,t+dt,h*sh+dh,w*sw+dw,c] * wgt[tap][n][c] )
- *                    (+ residual[b,t,h,w,n])
+ *                    * out_scale * rowscale[b*T+t, n]  (+ residual (+ residual2))
  *
  * `wgt` is packed [kt*kh*kw][Cout_pad][Cin_pad] (16-bit, Cin_pad = ceil64(Cin),
  * Cout_pad = ceil16(Cout)), zero padded.  Padding is k/2 in each dimension
@@ -77,6 +77,9 @@ typedef struct flair_conv_params {
   const float* bias;   /* [Cout] or NULL                                      */
   const float* rowbias;/* [B*T][rowbias_stride] fp32 or NULL                  */
   int rowbias_stride;
+  const float* rowscale;/* [B*T][rowscale_stride] fp32 or NULL: multiplies the  */
+  int rowscale_stride; /* activated result per (frame, channel) before the    */
+                       /* residual add (gate of sr3.TemporalWrapper2)         */
   const void* residual;/* same geometry as out, or NULL                       */
   int residual_dtype;  /* FLAIR_BF16 / FLAIR_F32 / FLAIR_F16                  */
   int residual_cstride;
@@ -244,7 +247,8 @@ int flair_attn_temporal(const void* qkv, void* out, const float* cq, const float
 /* ------------------------------------------------------------------------
  * Conditioning path (fp32) and input packing.
  * flair_timestep_embedding_f32: nn_new.py:103-121 (freqs table from the host).
- * flair_linear_f32: y = act_out(bias + act_in(x) Wt), Wt is [K][N] (time_embed
+ * flair_linear_f32: y = act_out(bias + act_in(x) Wt), Wt is [K][N]; act codes 0 none,
+ *   1 SiLU, 2 sigmoid (time_embed
  *   unet_new.py:979-984 and all ResBlock emb_layers :258-264 concatenated).
  * flair_pack_im2col6: cat([a,b], channel) (N,3,H,W) fp32 x2 -> [N][H][W][64]
  *   16-bit im2col (k = tap*6 + c) feeding the first conv (unet_new.py:993,1331).

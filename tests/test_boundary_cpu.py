@@ -101,3 +101,42 @@ def test_space_timesteps_variants():
     assert len(space_timesteps(300, [10, 15, 20])) == 45
     with pytest.raises(ValueError):
         space_timesteps(10, "20")
+
+
+def test_sr3_state_dict_matches_reference(golden):
+    from guided_diffusion.sr3 import UNet
+    fx = golden("unet_sr3.pt")
+    model = UNet(**fx["cfg"], dtype=torch.float16, use_checkpoint=True)
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert set(mine) == set(fx["keys"]), sorted(set(mine) ^ set(fx["keys"]))[:10]
+    assert mine == fx["keys"]
+    model.convert_to_fp16()
+    sd = model.state_dict()
+    assert sd["downs.1.res_block.block1.block.3.wrapped_module.weight"].dtype == torch.float16
+    assert sd["final_conv.block.3.wrapped_module.weight"].dtype == torch.float32
+    assert sd["noise_level_mlp.1.weight"].dtype == torch.float32
+
+
+def test_wrapped_model_dispatches_on_sr3(golden):
+    """respace._WrappedModel feeds the SR3 UNet the continuous noise level sqrt(alpha_bar) (respace.py:161-165)."""
+    from guided_diffusion import gaussian_diffusion as gd
+    from guided_diffusion.respace import SpacedDiffusion, _WrappedModel, space_timesteps
+    from guided_diffusion.sr3 import UNet
+    d = SpacedDiffusion(use_timesteps=space_timesteps(2000, "100", "uniform"),
+                        betas=gd.get_named_beta_schedule("face_bicubic", 2000), noise_schedule="face_bicubic",
+                        model_mean_type=gd.ModelMeanType.EPSILON, model_var_type=gd.ModelVarType.FIXED_SMALL,
+                        loss_type=gd.LossType.MSE)
+    seen = {}
+
+    class Fake(UNet):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+
+        def forward(self, x, level, **kw):
+            seen["level"] = level
+            return x
+
+    w = d._wrap_model(Fake())
+    assert isinstance(w, _WrappedModel)
+    w(torch.zeros(2, 3, 4, 4), torch.tensor([99, 0]))
+    assert torch.allclose(seen["level"], torch.tensor(d.sqrt_alphas_cumprod_prev[[100, 1]], dtype=torch.float32))

@@ -34,3 +34,25 @@ def test_video_mode_weight_map(oracle_model):
     out = m.forward(fx["x"], fx["video_t"], fx["low_res"][None], num_frames=4, rnn_input=None,
                     enable_cross_frames=True, vsrpp_weights=fx["vsrpp_weights"])
     assert rel_err(out, fx["video_out_weighted"]) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ SR3
+@pytest.fixture(scope="module")
+def sr3_oracle(golden):
+    from oracle.unet_sr3 import SR3UNetOracle
+    fx = golden("unet_sr3.pt")
+    sd = {k: synth.synthetic_tensor(k, shp, 1234) for k, shp in fx["keys"].items()}
+    return SR3UNetOracle(fx["cfg"], sd), fx
+
+
+def test_sr3_image_mode(sr3_oracle):
+    m, fx = sr3_oracle
+    out = m.forward(fx["x"], fx["image_level"], fx["low_res"][:, None], num_frames=1, enable_cross_frames=False)
+    assert rel_err(out, fx["image_out"]) < 2e-5
+
+
+def test_sr3_video_mode(sr3_oracle):
+    m, fx = sr3_oracle
+    out = m.forward(fx["x"], fx["video_level"], fx["low_res"][None], num_frames=4, enable_cross_frames=True,
+                    vsrpp_weights=fx["vsrpp_weights"])
+    assert rel_err(out, fx["video_out"]) < 2e-5

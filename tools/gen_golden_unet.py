@@ -118,6 +118,45 @@ def sampler_full(OUT, steps_t_start=-1, name="sampler_full.pt"):
                 "noise_seed": 2}, OUT / name)
 
 
+def sr3_golden(OUT):
+    """SR3 (bicubic) UNet: reference sr3.UNet on CPU, synthetic weights, image + video mode."""
+    import guided_diffusion.nn as rnn
+    import guided_diffusion.sr3 as rsr3
+    from flair_b200 import synth
+    assert "/root/reference" in rsr3.__file__
+
+    def cpu_attn(self, q, k, v):
+        s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) / math.sqrt(q.shape[-1])
+        return torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, dim=-1), v.float()).to(q.dtype)
+    rnn.FalshAttn.forward = cpu_attn
+    cfg = dict(image_size=64, in_channel=6, out_channel=3, inner_channel=64, norm_groups=16, channel_mults=(1, 2, 4, 8, 16),
+               attn_res=(16, 8), vsrpp_res=(64,), spatial_attn=False, temporal_attn=True, res_blocks=1, dropout=0.0,
+               dtype=torch.float32, cross_frame_module=True, use_checkpoint=False, num_frames=7, head_dim=64)
+    real = torch.cuda.is_available
+    torch.cuda.is_available = lambda: True
+    model = rsr3.UNet(**cfg)
+    torch.cuda.is_available = real
+    model.eval()
+    model.load_state_dict(synth.synthetic_state_dict(model, seed=1234))
+    keys = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(31)
+    clip = synth.synthetic_clip(4, 64, seed=6) * 2 - 1
+    x = torch.randn(4, 3, 64, 64, generator=g)
+    fx = {"cfg": {k: v for k, v in cfg.items() if k not in ("dtype", "use_checkpoint", "spatial_attn", "dropout")},
+          "keys": keys, "x": x, "low_res": clip}
+    lv = torch.tensor([0.9995, 0.93, 0.41, 0.012])
+    fx["image_level"] = lv
+    fx["image_out"] = model(x, lv, low_res_input=clip[:, None], num_frames=1, enable_cross_frames=False)
+    lvv = torch.full((4,), 0.37)
+    fx["video_level"] = lvv
+    wmap = (torch.rand(1, 4, 1, 64, 64, generator=g) > 0.5).float() * 0.07 + 0.93
+    fx["vsrpp_weights"] = wmap
+    fx["video_out"] = model(x, lvv, low_res_input=clip[None], num_frames=4, enable_cross_frames=True, vsrpp_weights=wmap)
+    for k in ("image_out", "video_out"):
+        print(k, tuple(fx[k].shape), float(fx[k].abs().mean()), float(fx[k].std()))
+    torch.save(fx, OUT / "unet_sr3.pt")
+    print("sr3 fixture written")
+
 if __name__ == "__main__":
     import sys
     from pathlib import Path
@@ -125,7 +164,9 @@ if __name__ == "__main__":
     import ref_env
     OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
     ref_env.setup()
-    if sys.argv[1] == "full":
+    if sys.argv[1] == "sr3":
+        sr3_golden(OUT)
+    elif sys.argv[1] == "full":
         sampler_full(OUT, -1, "sampler_full.pt")
     else:
         sampler_full(OUT, int(sys.argv[1]), f"sampler_t{sys.argv[1]}.pt")
