@@ -2,6 +2,7 @@
 // points.  See include/flair_b200.h for the conventions.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -27,6 +28,15 @@ int flair_num_sms() {
     if (sms <= 0) sms = 148;
   }
   return sms;
+}
+
+int flair_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FLAIR_PDL");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;  // measured: no gain inside CUDA graphs -> opt-in
+  }
+  return v;
 }
 
 flair_tmap_encode_fn flair_get_tmap_encode() {

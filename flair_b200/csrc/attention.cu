@@ -37,6 +37,7 @@ __device__ __forceinline__ uint32_t pk16(float a, float b, int dtype) {
 __global__ void __launch_bounds__(128)
 attn_spatial_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, const float* __restrict__ rowbias,
                     int rowbias_stride, int L, int heads, int qkv_cstride, int out_cstride, int dtype, float scale) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   __shared__ float Qs[16][kD];
   __shared__ float Ks[kD][33];
   __shared__ float Vs[32][kD];
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(256)
 attn_temporal_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, const float* __restrict__ cq,
                      const float* __restrict__ ck, const float* __restrict__ bv, int B, int T, long long P, int C,
                      int frames, int dtype, float scale) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const int heads = C / kD;
   const int half = frames / 2;
   const long long items = static_cast<long long>(B) * T * P * heads * 8;
@@ -195,9 +197,9 @@ extern "C" int flair_attn_spatial(const void* qkv, void* out, const float* rowbi
                 "flair_attn_spatial: bad sizes");
   FLAIR_REQUIRE(dtype == FLAIR_BF16 || dtype == FLAIR_F16, "flair_attn_spatial: 16-bit maps only");
   dim3 grid(ceil_div(L, 16), heads, N);
-  attn_spatial_kernel<<<grid, 128, 0, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out),
+  FLAIR_CHECK_CUDA(flair_launch(attn_spatial_kernel, dim3(grid), dim3(128), 0, stream, static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out),
                                                 rowbias, rowbias_stride, L, heads, qkv_cstride, out_cstride, dtype,
-                                                0.125f /* 64^-1/2 */);
+                                                0.125f /* 64^-1/2 */));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -213,8 +215,8 @@ extern "C" int flair_attn_temporal(const void* qkv, void* out, const float* cq, 
   long long blocks = ceil_div_ll(items, 256);
   const long long cap = static_cast<long long>(flair_num_sms()) * 8;
   if (blocks > cap) blocks = cap;
-  attn_temporal_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
-      static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), cq, ck, bv, B, T, P, C, frames, dtype, 0.125f);
+  FLAIR_CHECK_CUDA(flair_launch(attn_temporal_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, 
+      static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), cq, ck, bv, B, T, P, C, frames, dtype, 0.125f));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }

@@ -150,16 +150,13 @@ struct EpiPos {
 
 // One epilogue warp: accumulator columns [col_begin, col_end) of its 32 TMEM lanes, 16 at a time.
 // KIND: 0 fp16 NHWC, 1 bf16 NHWC, 2 fp32 NHWC, 3 fp32 NCHW.  ACT: FLAIR_ACT_*.
+// One 16-column chunk of one epilogue warp: bias, per-frame bias, activation, gate, residuals, store.
+// KIND: 0 fp16 NHWC, 1 bf16 NHWC, 2 fp32 NHWC, 3 fp32 NCHW.  ACT: FLAIR_ACT_*.
 template <int KIND, int ACT>
-__device__ __forceinline__ void epilogue_cols(const ConvKArgs& a, uint32_t t_addr, int col_begin, int col_end,
-                                              const EpiPos& pos, const float* __restrict__ sb) {
-  for (int c0 = col_begin; c0 < col_end; c0 += 16) {
-    uint32_t r[16];
-    __syncwarp();  // tcgen05.ld is warp-collective: reconverge after divergent stores
-    tmem_ld16(t_addr + static_cast<uint32_t>(c0), r);
-    tmem_ld_wait();
+__device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_t (&r)[16], int c0, const EpiPos& pos,
+                                               const float* __restrict__ sb) {
     const int n = pos.n0 + c0;
-    if (n >= a.Cout) continue;  // warp-uniform: padded columns
+    if (n >= a.Cout) return;  // warp-uniform: padded columns
     float v[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -202,7 +199,7 @@ __device__ __forceinline__ void epilogue_cols(const ConvKArgs& a, uint32_t t_add
       add_residual(v, a.residual, a.residual_dtype, pos.pix * a.residual_cstride + n, full16, a.Cout - n);
     if (a.residual2 != nullptr && pos.valid)
       add_residual(v, a.residual2, a.residual2_dtype, pos.pix * a.residual2_cstride + n, full16, a.Cout - n);
-    if (!pos.valid) continue;
+    if (!pos.valid) return;
     if (KIND == 3) {
       // fp32 planar output: (frame, n, h, w); lanes walk w -> coalesced per channel
       float* op = static_cast<float*>(a.out);
@@ -241,12 +238,29 @@ __device__ __forceinline__ void epilogue_cols(const ConvKArgs& a, uint32_t t_add
           if (n + j < a.Cout) op[j] = static_cast<uint16_t>(pack16(v[j], 0.0f, DT) & 0xFFFFu);
       }
     }
+}
+
+// One epilogue warp: accumulator columns [col_begin, col_end) of its 32 TMEM lanes; two 16-column TMEM
+// loads are in flight per wait.
+template <int KIND, int ACT>
+__device__ __forceinline__ void epilogue_cols(const ConvKArgs& a, uint32_t t_addr, int col_begin, int col_end,
+                                              const EpiPos& pos, const float* __restrict__ sb) {
+  for (int cc = col_begin; cc < col_end; cc += 32) {
+    uint32_t r0[16], r1[16];
+    __syncwarp();  // tcgen05.ld is warp-collective: reconverge after divergent stores
+    tmem_ld16(t_addr + static_cast<uint32_t>(cc), r0);
+    const bool second = cc + 16 < col_end;  // warp-uniform
+    tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);  // (columns past the tile are allocated, unused)
+    tmem_ld_wait();
+    epilogue_chunk<KIND, ACT>(a, r0, cc, pos, sb);
+    if (second) epilogue_chunk<KIND, ACT>(a, r1, cc + 16, pos, sb);
   }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvKArgs a) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(16) float s_bias[2][256];
   // carve: [resident weights (mode 2)] [stages][A][B] then barriers
@@ -288,6 +302,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   // tile walk of this CTA: (m_idx, n_idx) = f(local iteration)
   //   modes 0/1: linear tile id = blockIdx.x + i*gridDim.x, n fastest (neighbouring CTAs share A in L2)
@@ -371,6 +386,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // One lane issues; the per-MMA instruction count is what bounds small-N tiles (a first version
+    // rebuilt both 64-bit descriptors and did integer div/mod per MMA: ~150 cycles per issue, tensor pipe
+    // 6 % busy).  Descriptors are (constant high word, low word = smem address >> 4): the loop only adds
+    // small constants to the low words.
     const uint32_t idesc = umma_idesc_f16(kBlockM, static_cast<uint32_t>(a.n_tile), a.fmt);
     int stage = 0;
     uint32_t phase = 0;
@@ -378,50 +397,72 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(w_bar, 0);
       tc_fence_after();
     }
-    const uint32_t sw = smem_u32(smem_w);
+    const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // SBO, version, swizzle mode
+    const uint32_t desc_lo_flags = static_cast<uint32_t>(umma_desc_sw128(0));  // LBO field
+    const uint32_t stage0_lo = (smem_u32(smem) & 0x3FFFF) >> 4;
+    const uint32_t stage_step = stage_bytes >> 4;
+    const uint32_t a_step = a.a_bytes >> 4;
+    const uint32_t b_step = b_bytes >> 4;
+    const uint32_t w_lo = (smem_u32(smem_w) & 0x3FFFF) >> 4;
+    const uint32_t w_tap_step = static_cast<uint32_t>(a.kblocks) * b_step;  // resident weights: [tap][kb]
     for (int local = 0; local < my_tiles; ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * a.acc_cols);
-      for (int it = 0; it < k_iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          if (a.mode == 0) {
-            const uint64_t da = umma_desc_sw128(sa);
-            const uint64_t db = umma_desc_sw128(sa + a.a_bytes);
+      uint32_t accum = 0;  // first MMA of the tile overwrites the accumulator
+      if (a.mode == 0) {
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t alo = desc_lo_flags | (stage0_lo + static_cast<uint32_t>(stage) * stage_step);
+            const uint32_t blo = alo + a_step;
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               // +32 B per K step inside the 128 B swizzle row (encoded >> 4)
-              umma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                       idesc, (it | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, desc_hi | (alo + 2u * k), desc_hi | (blo + 2u * k), idesc, accum);
+              accum = 1;
             }
-          } else {
-            // it = (dti*3 + dwi)*kblocks + kb
-            const int kb = it % a.kblocks;
-            const int dwi = (it / a.kblocks) % 3;
-            const int dti = it / (3 * a.kblocks);
+            umma_commit(&empty_bar[stage]);
+            if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      } else {
+        int it = 0;
+        for (int dti = 0; dti < a.ntd; ++dti) {
+          for (int dwi = 0; dwi < 3; ++dwi) {
+            // resident weights of tap (dti, dhi=0, dwi), k-block 0
+            uint32_t wlo = desc_lo_flags | (w_lo + static_cast<uint32_t>(dti * 9 + dwi) * w_tap_step);
+            for (int kb = 0; kb < a.kblocks; ++kb, ++it, wlo += b_step) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              if (lane == 0) {
+                const uint32_t alo = desc_lo_flags | (stage0_lo + static_cast<uint32_t>(stage) * stage_step);
 #pragma unroll
-            for (int dhi = 0; dhi < 3; ++dhi) {
-              const uint64_t da = umma_desc_sw128(sa + static_cast<uint32_t>(dhi) * 2048u);  // 16 rows x 128 B
-              const int tap = (dti * 3 + dhi) * 3 + dwi;
-              const uint32_t bad = resident ? sw + static_cast<uint32_t>(tap * a.kblocks + kb) * b_bytes
-                                            : sa + a.a_bytes + static_cast<uint32_t>(dhi) * b_bytes;
-              const uint64_t db = umma_desc_sw128(bad);
+                for (int dhi = 0; dhi < 3; ++dhi) {
+                  // A: the dh tap is the same halo slab shifted by one 16-pixel row (2 KB); B: slab dhi of
+                  // this stage, or the resident slab of tap (dti, dhi, dwi) = base + dhi * 3 taps
+                  const uint32_t al = alo + static_cast<uint32_t>(dhi) * (2048u >> 4);
+                  const uint32_t bl = resident ? wlo + static_cast<uint32_t>(dhi) * 3u * w_tap_step
+                                               : alo + a_step + static_cast<uint32_t>(dhi) * b_step;
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                umma_f16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                         (it | dhi | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    umma_f16(d_tmem, desc_hi | (al + 2u * k), desc_hi | (bl + 2u * k), idesc, accum);
+                    accum = 1;
+                  }
+                }
+                umma_commit(&empty_bar[stage]);
+                if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+              }
+              __syncwarp();
+              if (++stage == a.stages) { stage = 0; phase ^= 1; }
             }
           }
-          umma_commit(&empty_bar[stage]);
-          if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
         }
-        __syncwarp();
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -437,6 +478,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int etid = threadIdx.x - 64;     // 0..255
     // epilogue kind: 0 = fp16 NHWC, 1 = bf16 NHWC, 2 = fp32 NHWC, 3 = fp32 NCHW
     const int kind = (a.out_layout == FLAIR_OUT_NCHW) ? 3 : (a.out_dtype == FLAIR_F32 ? 2 : (a.out_dtype == FLAIR_F16 ? 0 : 1));
+    int bias_n = -1, bias_buf = 0;
     for (int local = 0; local < my_tiles; ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -454,13 +496,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       pos.frame = static_cast<long long>(b) * a.T + t;
       pos.pix = (pos.frame * a.Ho + pos.h) * a.Wo + pos.w;
       pos.n0 = n_idx * a.n_tile;
-      // bias slice of this N tile -> shared (double-buffered with the accumulator); zero beyond Cout
-      float* sb = s_bias[acc];
-      if (etid < a.n_tile) {
-        const int n = pos.n0 + etid;
-        sb[etid] = (a.bias != nullptr && n < a.Cout) ? __ldg(a.bias + n) : 0.0f;
+      // bias slice of this N tile -> shared, zero beyond Cout.  Restaged only when the N tile changes
+      // (never, for one N tile or resident weights); two buffers so a restage cannot race the warps that
+      // are still finishing the previous tile.
+      if (n_idx != bias_n) {
+        bias_buf ^= 1;
+        bias_n = n_idx;
+        if (etid < a.n_tile) {
+          const int n = pos.n0 + etid;
+          s_bias[bias_buf][etid] = (a.bias != nullptr && n < a.Cout) ? __ldg(a.bias + n) : 0.0f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      const float* sb = s_bias[bias_buf];
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -569,8 +617,10 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   if (mode == 1 && env_mode != 1) {
     // resident weights: all slabs of one N tile (try the whole Cout first, then 64 columns) + >= 3 A stages
     const int budget = 227 * 1024 - 1024 - 256 - 2048 - 3 * 20480;
-    int cand[2] = {n_tile, 64};
-    for (int ci = 0; ci < 2; ++ci) {
+    // (shrinking the N tile to make the weights fit costs more in re-read A than residency saves:
+    //  128->128@128x128: 77 us resident/n64 vs 55 us streamed/n128)
+    int cand[1] = {n_tile};
+    for (int ci = 0; ci < 1; ++ci) {
       const int nt_ = cand[ci];
       if (nt_ > n_tile || Cout_pad % nt_ != 0) continue;
       if (static_cast<long long>(ntaps_total) * kblocks_ * nt_ * 128 <= budget) { mode = 2; n_tile = nt_; break; }
@@ -578,7 +628,9 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   }
   a.n_tile = n_tile;
   a.n_tiles = Cout_pad / n_tile;
-  a.tmem_cols = pow2_ceil(2 * n_tile < 32 ? 32 : 2 * n_tile);
+  // the epilogue reads TMEM 32 columns at a time: leave 16 columns of slack per accumulator buffer
+  // (n_tile = 256 splits into two 128-column halves and needs none)
+  a.tmem_cols = (n_tile == 256) ? 512 : pow2_ceil(2 * (n_tile + 16));
   a.acc_cols = a.tmem_cols / 2;
   a.Cout = p->Cout; a.Cout_pad = Cout_pad;
   a.kblocks = Cin_pad / kBlockK;
@@ -669,7 +721,7 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
     grid = (grid / a.n_tiles) * a.n_tiles;
     if (grid < a.n_tiles) grid = a.n_tiles;
   }
-  conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, a);
+  FLAIR_CHECK_CUDA(flair_launch(conv_igemm_kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, a));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }

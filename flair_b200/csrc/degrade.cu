@@ -18,6 +18,7 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 __global__ void __launch_bounds__(256)
 blur_down_kernel(const float* __restrict__ x, float* __restrict__ lr, const float* __restrict__ taps,
                  int k, int sf, int pre, int H, int W) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   extern __shared__ float sm[];
   const int h = H / sf, w = W / sf;
   const int r = k / 2;
@@ -51,6 +52,7 @@ blur_down_kernel(const float* __restrict__ x, float* __restrict__ lr, const floa
 __global__ void __launch_bounds__(256)
 filter_same_kernel(const float* __restrict__ x, const float* __restrict__ sub, float* __restrict__ out,
                    const float* __restrict__ taps, int k, int H, int W) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   extern __shared__ float sm[];
   const int r = k / 2;
   const int tile = 16;
@@ -83,6 +85,7 @@ filter_same_kernel(const float* __restrict__ x, const float* __restrict__ sub, f
 __global__ void __launch_bounds__(256)
 blur_up_kernel(const float* __restrict__ lr, float* __restrict__ hr, const float* __restrict__ taps,
                int k, int sf, int pre, int planes, int H, int W) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const int h = H / sf, w = W / sf, r = k / 2;
   const long long total = static_cast<long long>(planes) * H * W;
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(256)
 jpeg_kernel(int mode, const float* __restrict__ x, float* __restrict__ luma, float* __restrict__ chroma,
             float* __restrict__ out, const float* __restrict__ dct, const float* __restrict__ idct,
             const float* __restrict__ q_luma, const float* __restrict__ q_chroma, int h, int w) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   __shared__ float blk[6][8][8];
   __shared__ float tmp[6][8][8];
   __shared__ float s_d[64], s_di[64], s_q1[64], s_q2[64];
@@ -228,6 +232,7 @@ jpeg_kernel(int mode, const float* __restrict__ x, float* __restrict__ luma, flo
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float* __restrict__ A, long long sA, const float* __restrict__ B, long long sB,
                 const float* __restrict__ Sub, float* __restrict__ Cc, int M, int N, int K) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   __shared__ float As[32][33];
   __shared__ float Bs[32][33];
   const int b = blockIdx.z;
@@ -277,7 +282,7 @@ extern "C" int flair_blur_down_f32(const float* x, float* lr, const float* taps,
     FLAIR_CHECK_CUDA(cudaFuncSetAttribute(blur_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem)));
   dim3 grid(ceil_div(W / sf, 16), ceil_div(H / sf, 16), planes);
-  blur_down_kernel<<<grid, 256, smem, stream>>>(x, lr, taps, k, sf, pre, H, W);
+  FLAIR_CHECK_CUDA(flair_launch(blur_down_kernel, dim3(grid), dim3(256), smem, stream, x, lr, taps, k, sf, pre, H, W));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -292,7 +297,7 @@ extern "C" int flair_filter_same_f32(const float* x, const float* sub, float* ou
     FLAIR_CHECK_CUDA(cudaFuncSetAttribute(filter_same_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem)));
   dim3 grid(ceil_div(W, 16), ceil_div(H, 16), planes);
-  filter_same_kernel<<<grid, 256, smem, stream>>>(x, sub, out, taps, k, H, W);
+  FLAIR_CHECK_CUDA(flair_launch(filter_same_kernel, dim3(grid), dim3(256), smem, stream, x, sub, out, taps, k, H, W));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -308,7 +313,7 @@ extern "C" int flair_blur_up_f32(const float* lr, float* hr, const float* taps, 
   long long blocks = ceil_div_ll(total, 256);
   const long long cap = static_cast<long long>(flair_num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  blur_up_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(lr, hr, taps, k, sf, pre, planes, H, W);
+  FLAIR_CHECK_CUDA(flair_launch(blur_up_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, lr, hr, taps, k, sf, pre, planes, H, W));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -325,7 +330,7 @@ extern "C" int flair_jpeg_f32(int mode, const float* x, float* luma, float* chro
   if (mode != 2) FLAIR_REQUIRE(luma && chroma, "flair_jpeg_f32: coefficient planes are NULL");
   if (mode != 0) FLAIR_REQUIRE(out, "flair_jpeg_f32: out is NULL");
   dim3 grid(w / 16, h / 16, N);
-  jpeg_kernel<<<grid, 256, 0, stream>>>(mode, x, luma, chroma, out, dct, idct, q_luma, q_chroma, h, w);
+  FLAIR_CHECK_CUDA(flair_launch(jpeg_kernel, dim3(grid), dim3(256), 0, stream, mode, x, luma, chroma, out, dct, idct, q_luma, q_chroma, h, w));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -339,10 +344,10 @@ extern "C" int flair_sandwich_f32(const float* L, const float* X, const float* R
   FLAIR_REQUIRE(planes > 0 && planes < 65536 && p > 0 && q > 0 && r > 0 && s > 0,
                 "flair_sandwich_f32: bad sizes");
   dim3 g1(ceil_div(r, 32), ceil_div(p, 32), planes);
-  gemm_f32_kernel<<<g1, 256, 0, stream>>>(L, 0, X, static_cast<long long>(q) * r, nullptr, workspace, p, r, q);
+  FLAIR_CHECK_CUDA(flair_launch(gemm_f32_kernel, dim3(g1), dim3(256), 0, stream, L, 0, X, static_cast<long long>(q) * r, nullptr, workspace, p, r, q));
   FLAIR_CHECK_LAUNCH();
   dim3 g2(ceil_div(s, 32), ceil_div(p, 32), planes);
-  gemm_f32_kernel<<<g2, 256, 0, stream>>>(workspace, static_cast<long long>(p) * r, Rm, 0, sub, out, p, s, r);
+  FLAIR_CHECK_CUDA(flair_launch(gemm_f32_kernel, dim3(g2), dim3(256), 0, stream, workspace, static_cast<long long>(p) * r, Rm, 0, sub, out, p, s, r));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }

@@ -13,6 +13,7 @@ namespace {
 
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__ freqs,
                                           float* __restrict__ out, int N, int half) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * half) return;
   const int n = i / half, j = i % half;
@@ -26,6 +27,7 @@ template <int MB>
 __global__ void __launch_bounds__(256)
 linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ bias,
                   float* __restrict__ y, int M, int K, int N, int silu_in, int silu_out) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   extern __shared__ float xs[];  // [MB][K]
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   for (int m0 = 0; m0 < M; m0 += MB) {
@@ -62,6 +64,7 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ Wt, con
 __global__ void __launch_bounds__(256)
 pack_im2col6_kernel(const float* __restrict__ a, const float* __restrict__ b, uint16_t* __restrict__ out, int N,
                     int H, int W, int dtype) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long hw = static_cast<long long>(H) * W;
   const long long items = static_cast<long long>(N) * hw * 8;
   for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
@@ -107,7 +110,7 @@ extern "C" int flair_timestep_embedding_f32(const float* t, const float* freqs, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FLAIR_REQUIRE(t && freqs && out && N > 0 && dim > 0 && dim % 2 == 0, "flair_timestep_embedding_f32: bad arguments");
   const int half = dim / 2;
-  timestep_embedding_kernel<<<ceil_div(N * half, 128), 128, 0, stream>>>(t, freqs, out, N, half);
+  FLAIR_CHECK_CUDA(flair_launch(timestep_embedding_kernel, dim3(ceil_div(N * half, 128)), dim3(128), 0, stream, t, freqs, out, N, half));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -124,7 +127,7 @@ extern "C" int flair_linear_f32(const float* x, const float* Wt, const float* bi
     FLAIR_CHECK_CUDA(cudaFuncSetAttribute(linear_f32_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  linear_f32_kernel<MB><<<ceil_div(N, 256), 256, smem, stream>>>(x, Wt, bias, y, M, K, N, silu_in, silu_out);
+  FLAIR_CHECK_CUDA(flair_launch(linear_f32_kernel<MB>, dim3(ceil_div(N, 256)), dim3(256), smem, stream, x, Wt, bias, y, M, K, N, silu_in, silu_out));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -137,7 +140,7 @@ extern "C" int flair_pack_im2col6(const float* a, const float* b, void* out, int
   long long blocks = ceil_div_ll(items, 256);
   const long long cap = static_cast<long long>(flair_num_sms()) * 8;
   if (blocks > cap) blocks = cap;
-  pack_im2col6_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(a, b, static_cast<uint16_t*>(out), N, H, W, dtype);
+  FLAIR_CHECK_CUDA(flair_launch(pack_im2col6_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, a, b, static_cast<uint16_t*>(out), N, H, W, dtype));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }

@@ -63,6 +63,7 @@ __device__ __forceinline__ void store8(void* base, long long elem_off, int dtype
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const void* __restrict__ x, int dtype, long long P, int C, int cstride, int groups,
                 int ppb, long long pix_per_chunk, float2* __restrict__ partial) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   extern __shared__ float sm[];  // [2][ppb][C]
   const int vecs = C / 8;
   const int cv = threadIdx.x % vecs, pl = threadIdx.x / vecs;
@@ -117,6 +118,7 @@ struct ApplyArgs {
 
 // grid (blocks, B)
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ ApplyArgs a) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   __shared__ float s_mean[kGroupsMax], s_rstd[kGroupsMax];
   const int b = blockIdx.y;
   const int cpg = a.C / a.groups;
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ A
 __global__ void __launch_bounds__(256)
 copy_channels_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long P, int vecs,
                      int src_vstride, int dst_vstride, int dst_voff) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long items = P * vecs;
   for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
        it += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -264,8 +267,8 @@ extern "C" int flair_gn_stats(const void* x, int dtype, int B, long long P, int 
   const long long ppc = ceil_div_ll(P, nchunks);
   const size_t smem = sizeof(float) * 2 * ppb * C;
   dim3 grid(nchunks, B);
-  gn_stats_kernel<<<grid, vecs * ppb, smem, stream>>>(x, dtype, P, C, cstride, groups, ppb, ppc,
-                                                     reinterpret_cast<float2*>(partial));
+  FLAIR_CHECK_CUDA(flair_launch(gn_stats_kernel, dim3(grid), dim3(vecs * ppb), smem, stream, x, dtype, P, C, cstride, groups, ppb, ppc,
+                                                     reinterpret_cast<float2*>(partial)));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -290,7 +293,7 @@ extern "C" int flair_gn_apply(const flair_gn_apply_params* p, void* stream_) {
   const int Hi = (p->resample == 2) ? p->H / 2 : p->H, Wi = (p->resample == 2) ? p->W / 2 : p->W;
   const long long items = static_cast<long long>(p->T) * Hi * Wi * (p->C / 8);
   dim3 grid(ew_blocks(items, 8), p->B);
-  gn_apply_kernel<<<grid, 256, 0, stream>>>(a);
+  FLAIR_CHECK_CUDA(flair_launch(gn_apply_kernel, dim3(grid), dim3(256), 0, stream, a));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -304,9 +307,9 @@ extern "C" int flair_copy_channels(const void* src, void* dst, long long pixels,
                     dst_cstride % epv == 0 && dst_coffset % epv == 0,
                 "flair_copy_channels: channel counts/offsets must be multiples of %d", epv);
   const int vecs = channels / epv;
-  copy_channels_kernel<<<ew_blocks(pixels * vecs, 8), 256, 0, stream>>>(
+  FLAIR_CHECK_CUDA(flair_launch(copy_channels_kernel, dim3(ew_blocks(pixels * vecs, 8)), dim3(256), 0, stream, 
       static_cast<const uint4*>(src), static_cast<uint4*>(dst), pixels, vecs, src_cstride / epv,
-      dst_cstride / epv, dst_coffset / epv);
+      dst_cstride / epv, dst_coffset / epv));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }

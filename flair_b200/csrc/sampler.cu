@@ -70,6 +70,7 @@ __device__ __forceinline__ float up_at(const UpdArgs& a, const float* q, int i, 
 }
 
 __global__ void __launch_bounds__(256) sampler_update_kernel(const __grid_constant__ UpdArgs a) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long hw = static_cast<long long>(a.H) * a.W;
   const long long total4 = static_cast<long long>(a.N) * 3 * hw / 4;
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total4;
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(256)
 pred_xstart_kernel(const float* __restrict__ x_t, const float* __restrict__ model_out, int model_ch,
                    const float* __restrict__ coef, const long long* t_arr, int t_host,
                    float* __restrict__ x0, int N, long long hw, int clip) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long total4 = static_cast<long long>(N) * 3 * hw / 4;
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total4;
        v += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -162,6 +164,7 @@ pred_xstart_kernel(const float* __restrict__ x_t, const float* __restrict__ mode
 __global__ void __launch_bounds__(256)
 axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float alpha, float beta,
              float* __restrict__ out, long long n4) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n4;
        v += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(x) + v);
@@ -211,7 +214,7 @@ extern "C" int flair_sampler_update_f32(const flair_update_params* p, void* stre
   a.sample = p->sample; a.pred_xstart = p->pred_xstart;
   a.N = p->N; a.H = p->H; a.W = p->W; a.clip = p->clip_denoised;
   const long long total4 = static_cast<long long>(p->N) * 3 * p->H * p->W / 4;
-  sampler_update_kernel<<<ew_grid(total4), 256, 0, stream>>>(a);
+  FLAIR_CHECK_CUDA(flair_launch(sampler_update_kernel, dim3(ew_grid(total4)), dim3(256), 0, stream, a));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -223,8 +226,8 @@ extern "C" int flair_pred_xstart_f32(const float* x_t, const float* model_out, i
   FLAIR_REQUIRE(x_t && model_out && coef && x0, "flair_pred_xstart_f32: null pointer");
   FLAIR_REQUIRE((static_cast<long long>(H) * W) % 4 == 0, "flair_pred_xstart_f32: H*W must be a multiple of 4");
   const long long hw = static_cast<long long>(H) * W;
-  pred_xstart_kernel<<<ew_grid(static_cast<long long>(N) * 3 * hw / 4), 256, 0, stream>>>(
-      x_t, model_out, model_ch, coef, t_arr, t, x0, N, hw, clip_denoised);
+  FLAIR_CHECK_CUDA(flair_launch(pred_xstart_kernel, dim3(ew_grid(static_cast<long long>(N) * 3 * hw / 4)), dim3(256), 0, stream, 
+      x_t, model_out, model_ch, coef, t_arr, t, x0, N, hw, clip_denoised));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -233,7 +236,7 @@ extern "C" int flair_axpby_f32(const float* x, const float* y, float alpha, floa
                                long long n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FLAIR_REQUIRE(x && y && out && n % 4 == 0, "flair_axpby_f32: null pointer or n not a multiple of 4");
-  axpby_kernel<<<ew_grid(n / 4), 256, 0, stream>>>(x, y, alpha, beta, out, n / 4);
+  FLAIR_CHECK_CUDA(flair_launch(axpby_kernel, dim3(ew_grid(n / 4)), dim3(256), 0, stream, x, y, alpha, beta, out, n / 4));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -246,6 +249,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 dc_apply_kernel(const float* __restrict__ x0, const float* __restrict__ R, const float* __restrict__ gamma_arr,
                 float gamma_host, float* __restrict__ out, long long hw3, long long total4, int clip) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total4;
        v += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long e = v * 4;
@@ -269,6 +273,7 @@ mean_variance_kernel(const float* __restrict__ x_t, const float* __restrict__ x0
                      const float* __restrict__ var_values, int model_ch, const float* __restrict__ tab,
                      const long long* __restrict__ t_arr, int t_host, float* __restrict__ mean,
                      float* __restrict__ variance, float* __restrict__ log_variance, int N, long long hw) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long total = static_cast<long long>(N) * 3 * hw;
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
        e += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -301,8 +306,8 @@ extern "C" int flair_dc_apply_f32(const float* x0, const float* R, const float* 
   const long long hw3 = 3LL * H * W;
   FLAIR_REQUIRE(hw3 % 4 == 0, "flair_dc_apply_f32: 3*H*W must be a multiple of 4");
   const long long total4 = static_cast<long long>(N) * hw3 / 4;
-  dc_apply_kernel<<<ew_grid(total4), 256, 0, stream>>>(x0, R, gamma_arr, gamma, out, hw3, total4,
-                                                       clip_denoised);
+  FLAIR_CHECK_CUDA(flair_launch(dc_apply_kernel, dim3(ew_grid(total4)), dim3(256), 0, stream, x0, R, gamma_arr, gamma, out, hw3, total4,
+                                                       clip_denoised));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -315,8 +320,8 @@ extern "C" int flair_mean_variance_f32(const float* x_t, const float* x0, const 
   FLAIR_REQUIRE(x_t && x0 && tab && mean && variance && log_variance, "flair_mean_variance_f32: null pointer");
   if (learned_range) FLAIR_REQUIRE(model_out && model_ch == 6, "flair_mean_variance_f32: learned range needs 6 channels");
   const long long hw = static_cast<long long>(H) * W;
-  mean_variance_kernel<<<ew_grid(static_cast<long long>(N) * 3 * hw), 256, 0, stream>>>(
-      x_t, x0, learned_range ? model_out : nullptr, model_ch, tab, t_arr, t, mean, variance, log_variance, N, hw);
+  FLAIR_CHECK_CUDA(flair_launch(mean_variance_kernel, dim3(ew_grid(static_cast<long long>(N) * 3 * hw)), dim3(256), 0, stream, 
+      x_t, x0, learned_range ? model_out : nullptr, model_ch, tab, t_arr, t, mean, variance, log_variance, N, hw));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }

@@ -47,6 +47,7 @@ __device__ __forceinline__ void st8(uint16_t* p, int dtype, const float (&v)[8])
 __global__ void __launch_bounds__(256)
 flow_warp_kernel(const uint16_t* __restrict__ x, const float* __restrict__ flow, uint16_t* __restrict__ out, int N,
                  int H, int W, int C, int x_cstride, int out_cstride, int dtype) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const int vecs = C / 8;
   const long long hw = static_cast<long long>(H) * W;
   const long long items = static_cast<long long>(N) * hw * vecs;
@@ -83,6 +84,7 @@ flow_warp_kernel(const uint16_t* __restrict__ x, const float* __restrict__ flow,
 __global__ void __launch_bounds__(256)
 flow_compose_kernel(const float* __restrict__ f2, const float* __restrict__ f1, float* __restrict__ out, int N, int H,
                     int W) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long hw = static_cast<long long>(H) * W;
   const long long items = static_cast<long long>(N) * hw;
   for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
@@ -115,6 +117,7 @@ flow_compose_kernel(const float* __restrict__ f2, const float* __restrict__ f1, 
 __global__ void __launch_bounds__(256)
 planes_to_cl_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int N, int Cs, long long hw,
                     int dst_cstride, int dst_coff, int dtype) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long items = static_cast<long long>(N) * hw * Cs;
   for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
        it += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -156,6 +159,7 @@ deform_im2col_kernel(const uint16_t* __restrict__ xa, const uint16_t* __restrict
                      const uint16_t* __restrict__ om, int om_cstride, int om_dtype, const float* __restrict__ flow1,
                      const float* __restrict__ flow2, uint16_t* __restrict__ cols, int N, int H, int W, int C, int dg,
                      float mrm, int dtype) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   extern __shared__ float dsm[];  // [kDefPix][3][dg*9]: dy | dx | mask
   const int pairs = dg * 9;
   const int nch = pairs * 3;  // channels of the offset-net output actually used
@@ -255,6 +259,7 @@ deform_im2col_kernel(const uint16_t* __restrict__ xa, const uint16_t* __restrict
 __global__ void __launch_bounds__(256)
 scale_pixels_kernel(uint16_t* __restrict__ x, const float* __restrict__ wmap, long long pixels, int C, int cstride,
                     int dtype) {
+  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const int vecs = C / 8;
   const long long items = pixels * vecs;
   for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
@@ -285,8 +290,8 @@ extern "C" int flair_flow_warp(const void* x, const float* flow, void* out, int 
                                int x_cstride, int out_cstride, int dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FLAIR_REQUIRE(x && flow && out && C % 8 == 0 && x_cstride % 8 == 0 && out_cstride % 8 == 0, "flair_flow_warp: bad arguments");
-  flow_warp_kernel<<<blocks_for(static_cast<long long>(N) * H * W * (C / 8)), 256, 0, stream>>>(
-      static_cast<const uint16_t*>(x), flow, static_cast<uint16_t*>(out), N, H, W, C, x_cstride, out_cstride, dtype);
+  FLAIR_CHECK_CUDA(flair_launch(flow_warp_kernel, dim3(blocks_for(static_cast<long long>(N) * H * W * (C / 8))), dim3(256), 0, stream, 
+      static_cast<const uint16_t*>(x), flow, static_cast<uint16_t*>(out), N, H, W, C, x_cstride, out_cstride, dtype));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -294,7 +299,7 @@ extern "C" int flair_flow_warp(const void* x, const float* flow, void* out, int 
 extern "C" int flair_flow_compose_f32(const float* f2, const float* f1, float* out, int N, int H, int W, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FLAIR_REQUIRE(f2 && f1 && out, "flair_flow_compose_f32: null pointer");
-  flow_compose_kernel<<<blocks_for(static_cast<long long>(N) * H * W), 256, 0, stream>>>(f2, f1, out, N, H, W);
+  FLAIR_CHECK_CUDA(flair_launch(flow_compose_kernel, dim3(blocks_for(static_cast<long long>(N) * H * W)), dim3(256), 0, stream, f2, f1, out, N, H, W));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -304,8 +309,8 @@ extern "C" int flair_planes_to_cl(const float* src, void* dst, int N, int Cs, in
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FLAIR_REQUIRE(src && dst, "flair_planes_to_cl: null pointer");
   const long long hw = static_cast<long long>(H) * W;
-  planes_to_cl_kernel<<<blocks_for(N * hw * Cs), 256, 0, stream>>>(src, static_cast<uint16_t*>(dst), N, Cs, hw,
-                                                                  dst_cstride, dst_coffset, dtype);
+  FLAIR_CHECK_CUDA(flair_launch(planes_to_cl_kernel, dim3(blocks_for(N * hw * Cs)), dim3(256), 0, stream, src, static_cast<uint16_t*>(dst), N, Cs, hw,
+                                                                  dst_cstride, dst_coffset, dtype));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -323,10 +328,10 @@ extern "C" int flair_deform_im2col(const void* xa, const void* xb, int xa_cstrid
                 "flair_deform_im2col: unsupported deform_groups=%d", deform_groups);
   const long long total_pix = static_cast<long long>(N) * H * W;
   const size_t smem = sizeof(float) * kDefPix * deform_groups * 27;
-  deform_im2col_kernel<<<static_cast<unsigned>(ceil_div_ll(total_pix, kDefPix)), 256, smem, stream>>>(
+  FLAIR_CHECK_CUDA(flair_launch(deform_im2col_kernel, dim3(static_cast<unsigned>(ceil_div_ll(total_pix, kDefPix))), dim3(256), smem, stream, 
       static_cast<const uint16_t*>(xa), static_cast<const uint16_t*>(xb), xa_cstride, xb_cstride,
       static_cast<const uint16_t*>(om), om_cstride, om_dtype, flow1, flow2, static_cast<uint16_t*>(cols), N, H, W, C,
-      deform_groups, max_residue_magnitude, dtype);
+      deform_groups, max_residue_magnitude, dtype));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -335,8 +340,8 @@ extern "C" int flair_scale_pixels(void* x, const float* wmap, long long pixels, 
                                   void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FLAIR_REQUIRE(x && wmap && C % 8 == 0, "flair_scale_pixels: bad arguments");
-  scale_pixels_kernel<<<blocks_for(pixels * (C / 8)), 256, 0, stream>>>(static_cast<uint16_t*>(x), wmap, pixels, C,
-                                                                       cstride, dtype);
+  FLAIR_CHECK_CUDA(flair_launch(scale_pixels_kernel, dim3(blocks_for(pixels * (C / 8))), dim3(256), 0, stream, static_cast<uint16_t*>(x), wmap, pixels, C,
+                                                                       cstride, dtype));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }

@@ -8,8 +8,10 @@ from guided_diffusion.unet_new import UNetModel
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 mode = sys.argv[2] if len(sys.argv) > 2 else "video"
 SZ = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+import os
+NOVSR = bool(int(os.environ.get('NOVSR', '0')))
 cfg = dict(image_size=SZ, in_channels=6, model_channels=128, out_channels=6, num_res_blocks=2,
-           attention_resolutions=(16, 32, 64), rnn_resolutions=(1, 2), channel_mult=(0.5, 1, 1, 2, 2, 4, 4),
+           attention_resolutions=(16, 32, 64), rnn_resolutions=() if NOVSR else (1, 2), channel_mult=(0.5, 1, 1, 2, 2, 4, 4),
            use_fp16=True, num_head_channels=64, resblock_updown=True, use_scale_shift_norm=True,
            temporal_block=True, use_checkpoint=True)
 t0 = time.time()
