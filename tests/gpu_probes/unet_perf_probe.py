@@ -18,6 +18,7 @@ t0 = time.time()
 model = UNetModel(**cfg)
 model.load_state_dict(synth.synthetic_state_dict(model))
 model.convert_to_fp16(); model.eval().cuda()
+model.use_cuda_graph = not bool(int(os.environ.get('NOGRAPH', '0')))
 print("model ready", time.time() - t0, flush=True)
 dev = "cuda"
 clip = (synth.synthetic_clip(T, SZ) * 2 - 1).to(dev)
