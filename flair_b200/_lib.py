@@ -27,6 +27,7 @@ class ConvParams(C.Structure):
         ("out", C.c_void_p), ("out_dtype", C.c_int), ("out_layout", C.c_int),
         ("out_cstride", C.c_int), ("act", C.c_int), ("in_dtype", C.c_int),
         ("out_scale", C.c_float), ("gn_partial", C.c_void_p), ("gn_groups", C.c_int),
+        ("out2", C.c_void_p), ("out2_group_channels", C.c_int), ("out2_group_stride", C.c_longlong),
     ]
 
 
@@ -51,6 +52,17 @@ class GNApplyParams(C.Structure):
         ("B", C.c_int), ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("groups", C.c_int),
         ("x_cstride", C.c_int), ("out_cstride", C.c_int),
         ("norm", C.c_int), ("silu", C.c_int), ("resample", C.c_int), ("eps", C.c_float),
+    ]
+
+
+class DeformConvParams(C.Structure):
+    _fields_ = [
+        ("xa", C.c_void_p), ("xa_gstride", C.c_longlong), ("xa_pstride", C.c_longlong), ("xa_nstride", C.c_longlong),
+        ("xb", C.c_void_p), ("xb_gstride", C.c_longlong), ("xb_pstride", C.c_longlong), ("xb_nstride", C.c_longlong),
+        ("om", C.c_void_p), ("om_cstride", C.c_int), ("flow1", C.c_void_p), ("flow2", C.c_void_p),
+        ("wgt", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("out_cstride", C.c_int),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("deform_groups", C.c_int),
+        ("max_residue_magnitude", C.c_float), ("dtype", C.c_int),
     ]
 
 
@@ -95,6 +107,7 @@ def lib() -> C.CDLL:
         _lib.flair_planes_to_cl.argtypes = [vp, vp, i, i, i, i, i, i, i, vp]
         _lib.flair_deform_im2col.argtypes = [vp, vp, i, i, vp, i, i, vp, vp, vp, i, i, i, i, i, f, i, vp]
         _lib.flair_scale_pixels.argtypes = [vp, vp, ll, i, i, i, vp]
+        _lib.flair_deform_conv.argtypes = [C.POINTER(DeformConvParams), vp]
     return _lib
 
 

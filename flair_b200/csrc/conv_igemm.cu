@@ -74,6 +74,9 @@ struct ConvKArgs {
   uint32_t fmt;
   float* gn_partial;
   int gn_groups;
+  uint16_t* out2;          // optional group-major copy of a 16-bit NHWC output: [Cout/out2_gs][pixels][out2_gs]
+  int out2_gs;
+  long long out2_gstride;  // elements between group planes
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -231,6 +234,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_
           u.z = pack16(v[8 * q + 4], v[8 * q + 5], DT);
           u.w = pack16(v[8 * q + 6], v[8 * q + 7], DT);
           reinterpret_cast<uint4*>(op)[q] = u;
+          if (a.out2 != nullptr) {  // group-major planes for the deformable gather (flair_deform_conv)
+            const int ch = n + 8 * q;
+            *reinterpret_cast<uint4*>(a.out2 + (ch / a.out2_gs) * a.out2_gstride + pos.pix * a.out2_gs + (ch % a.out2_gs)) = u;
+          }
         }
       } else {
 #pragma unroll
@@ -656,6 +663,12 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   a.out_scale = (p->out_scale == 0.0f) ? 1.0f : p->out_scale;
   a.fmt = (p->in_dtype == FLAIR_BF16) ? 1u : 0u;
   a.gn_partial = nullptr; a.gn_groups = 0;
+  a.out2 = static_cast<uint16_t*>(p->out2); a.out2_gs = p->out2_group_channels; a.out2_gstride = p->out2_group_stride;
+  if (p->out2 != nullptr)
+    FLAIR_REQUIRE(p->out_layout == FLAIR_OUT_NHWC && p->out_dtype != FLAIR_F32 && p->Cout % 16 == 0 &&
+                      (p->out2_group_channels == 8 || p->out2_group_channels == 16) && p->out2_group_stride % 8 == 0 &&
+                      (reinterpret_cast<uintptr_t>(p->out2) & 15) == 0,
+                  "flair_conv_igemm: out2 needs a 16-bit NHWC output, Cout %% 16 == 0, 8 or 16 channels per group");
 
   const uint32_t b_bytes = static_cast<uint32_t>(n_tile) * kBlockK * 2;  // multiple of 2 KB (n_tile % 16 == 0)
   a.mode = mode;

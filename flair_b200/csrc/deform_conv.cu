@@ -1,0 +1,480 @@
+// Fused modulated deformable convolution (3x3, pad 1, stride 1, 16 deform groups) for sm_100a:
+// the bilinear gather IS the A-operand producer of a tcgen05 GEMM, the im2col matrix never exists.
+//
+// Replaces SecondOrderDeformableAlignment.forward after the offset net (reference
+// guided_diffusion/unet_new.py:874-898; unet.py:469-492): offset = mrm * tanh(cat(o1, o2)) + flipped
+// flows, mask = sigmoid(.), torchvision.ops.deform_conv2d(cat(feat_prop, feat_n2), offset, weight,
+// bias, padding 1, mask).  The previous two-kernel version (flair_deform_im2col + 1x1 GEMM) wrote
+// and re-read 18C x 2 B per pixel (151 MB per 256x256 frame at C = 64) and was bound by L1
+// wavefronts of scattered 16-byte gathers (153 us per launch, 28 % of the whole UNet forward).
+//
+// Roles (14 warps): warp 0 = TMA (weight slabs + offset rows), warp 1 = tcgen05.mma issuer,
+// warps 2..5 = epilogue (TMEM -> +bias -> 16-bit NHWC), warps 6..13 = gather producers.
+// M tile = 128 consecutive pixels, N = C, K = 9 taps x 2C walked in 64-channel k-blocks
+// (k = tap * 2C + channel of cat(xa, xb), the layout flair_deform_im2col used, so the packed
+// weight is unchanged).  A producer warp owns 32 pixel rows x the 8 deform groups of one source: per tap
+// it reads its (dy, dx, mask) triples from the TMA-staged offset rows, gathers 4 corners x (C/64) 16-byte vectors
+// per group, blends in fp32 and writes the 16-byte chunks straight into the 128B-swizzled K-major
+// operand tile the MMA consumes (generic-proxy stores + fence.proxy.async + mbarrier arrive).
+//
+// Source layout.  With NHWC sources the 32 lanes of a gather (32 neighbouring pixels, one deform
+// group) touch 32 different 128-byte lines.  The caller may instead pass group-major planes
+// [group][pixel][C/8 channels] (conv epilogue `out2`, see flair_conv_params): neighbouring pixels of
+// one group are then contiguous and a warp-wide gather touches ~4-8 lines.  Both are described by
+// (group stride, pixel stride) in elements.
+//
+// Offset-net output layout.  The caller permutes the output channels of the last offset conv at
+// weight-pack time so that the 48 values one tap needs are contiguous per pixel:
+//   channel = tap*48 + quad*12 + kind*4 + gi,  group = quad*4 + gi,  kind 0 = dy, 1 = dx, 2 = mask
+// (reference order: dy/dx at (group*9 + tap)*2 + {0,1}, mask at 288 + group*9 + tap).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "../../include/flair_b200.h"
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kProdWarps = 16;
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = 32 * (2 + kEpiWarps + kProdWarps);  // 704
+constexpr uint32_t kABytes = kTileM * kBlockK * 2;  // 16 KB
+constexpr int kOmStages = 3;
+constexpr uint32_t kOmBytes = kTileM * 48 * 2;  // one tap: 128 pixels x 48 halves
+constexpr int kGroups = 16;
+
+struct DeformArgs {
+  const uint16_t* src[2];
+  long long src_gstride[2], src_nstride[2];
+  int src_pstride[2];
+  const float* flow1;
+  const float* flow2;
+  const float* bias;
+  uint16_t* out;
+  long long out_cstride;
+  int N, H, W, C;
+  int kpt;   // k-blocks per tap (2C / 64)
+  int tiles;
+  int stages;
+  uint32_t b_bytes, stage_bytes;
+  float mrm;
+  uint32_t fmt;
+};
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Explicit shared-window accesses (32-bit addresses, STS/LDS instead of generic ST.E/LD.E).
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool BF16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  if (BF16) return unpack_bf16x2(u);
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if (BF16) return pack_bf16x2(lo, hi);
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Blend of the 4 bilinear corners of one 16-byte (8-channel) vector.
+//   fp16: packed half2 FMAs.  The reference runs torchvision's deform_conv2d in fp16 here (bilinear_interpolate is
+//         templated on scalar_t = Half: every product and sum is rounded to fp16), so fp16 accumulation is not a
+//         precision loss against it; it halves the instruction count of this issue-bound loop.
+//   bf16: fp32 accumulation (bf16 FMAs would add ~1e-2 relative error per sample).
+template <bool BF16>
+__device__ __forceinline__ uint4 blend4(const uint4 (&v)[4], const float (&w)[4]) {
+  uint4 o;
+  if (!BF16) {
+    __half2 acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const __half2 wc = __float2half2_rn(w[c]);
+      const __half2* hv = reinterpret_cast<const __half2*>(&v[c]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] = (c == 0) ? __hmul2(wc, hv[e]) : __hfma2(wc, hv[e], acc[e]);
+    }
+    o.x = *reinterpret_cast<uint32_t*>(&acc[0]); o.y = *reinterpret_cast<uint32_t*>(&acc[1]);
+    o.z = *reinterpret_cast<uint32_t*>(&acc[2]); o.w = *reinterpret_cast<uint32_t*>(&acc[3]);
+  } else {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t uu[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16x2(uu[e]);
+        acc[2 * e] = fmaf(w[c], f.x, acc[2 * e]);
+        acc[2 * e + 1] = fmaf(w[c], f.y, acc[2 * e + 1]);
+      }
+    }
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  }
+  return o;
+}
+
+template <int VPG, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOM,
+                   const __grid_constant__ DeformArgs a) {
+  pdl_sync();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(16) float s_bias[256];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_om = smem + static_cast<size_t>(a.stages) * a.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_om + kOmStages * kOmBytes);
+  uint64_t* full_bar = bars;                    // [stages]  producers (+ weight TMA) -> MMA
+  uint64_t* empty_bar = bars + a.stages;        // [stages]  MMA -> producers / TMA
+  uint64_t* om_full = empty_bar + a.stages;     // [kOmStages]
+  uint64_t* om_empty = om_full + kOmStages;     // [kOmStages]
+  uint64_t* tfull_bar = om_empty + kOmStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int n_tile = 64 * VPG;          // = C
+  constexpr int tmem_cols = 2 * n_tile;     // 128 or 256
+  // producer warps = 4 row quarters x 4 group quads.  C = 64: a k-block (one tap, one source) holds 8 groups ->
+  // filled by 2 quads x 4 quarters; C = 128: 4 groups per k-block -> 1 quad x 4 quarters.
+  constexpr int prod_arrivals = (VPG == 1) ? 8 : 4;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOM);
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full_bar[s], prod_arrivals * 32 + 1);  // every producer lane arrives after its own proxy fence
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kOmStages; ++s) {
+      mbar_init(&om_full[s], 1);
+      mbar_init(&om_empty[s], kProdWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(tmem_cols));
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + n_tile) {
+    const int i = threadIdx.x - 64;
+    s_bias[i] = (a.bias != nullptr) ? __ldg(a.bias + i) : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int my_tiles = (static_cast<int>(blockIdx.x) < a.tiles)
+                           ? (a.tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+  const int kb_per_tile = 9 * a.kpt;
+  const int hw = a.H * a.W;
+  const int total_pix = a.N * hw;
+
+  if (warp == 0) {
+    // ===================== TMA: offset rows per tap, weight slab per k-block =====================
+    if (lane == 0) {
+      int stage = 0, os = 0;
+      uint32_t phase = 0, ophase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int pix0 = tile * kTileM;
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&om_empty[os], ophase ^ 1);
+          mbar_expect_tx(&om_full[os], kOmBytes);
+          tma_load_2d(smem_om + os * kOmBytes, &tmOM, &om_full[os], tap * 48, pix0);
+          if (++os == kOmStages) { os = 0; ophase ^= 1; }
+          for (int j = 0; j < a.kpt; ++j) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], a.b_bytes);
+            tma_load_2d(smem + static_cast<size_t>(stage) * a.stage_bytes + kABytes, &tmB, &full_bar[stage],
+                        (tap * a.kpt + j) * kBlockK, 0);
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_f16(kTileM, static_cast<uint32_t>(n_tile), a.fmt);
+    const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo_flags = static_cast<uint32_t>(umma_desc_sw128(0));
+    const uint32_t stage0_lo = (smem_u32(smem) & 0x3FFFF) >> 4;
+    const uint32_t stage_step = a.stage_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int local = 0; local < my_tiles; ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * n_tile);
+      uint32_t accum = 0;
+      for (int it = 0; it < kb_per_tile; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t alo = desc_lo_flags | (stage0_lo + static_cast<uint32_t>(stage) * stage_step);
+          const uint32_t blo = alo + (kABytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            umma_f16(d_tmem, desc_hi | (alo + 2u * k), desc_hi | (blo + 2u * k), idesc, accum);
+            accum = 1;
+          }
+          umma_commit(&empty_bar[stage]);
+          if (it == kb_per_tile - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    for (int local = 0; local < my_tiles; ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int tile = blockIdx.x + local * gridDim.x;
+      const long long pix = static_cast<long long>(tile) * kTileM + row;
+      const bool valid = pix < total_pix;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * n_tile) + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < n_tile; cc += 32) {
+        uint32_t r0[16], r1[16];
+        __syncwarp();
+        tmem_ld16(t_addr + static_cast<uint32_t>(cc), r0);
+        tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);
+        tmem_ld_wait();
+        if (valid) {
+          uint16_t* op = a.out + pix * a.out_cstride + cc;
+          uint4 u[4];
+          uint32_t* uw = reinterpret_cast<uint32_t*>(u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uw[j] = pack2<BF16>(__uint_as_float(r0[2 * j]) + s_bias[cc + 2 * j], __uint_as_float(r0[2 * j + 1]) + s_bias[cc + 2 * j + 1]);
+            uw[8 + j] = pack2<BF16>(__uint_as_float(r1[2 * j]) + s_bias[cc + 16 + 2 * j],
+                                    __uint_as_float(r1[2 * j + 1]) + s_bias[cc + 16 + 2 * j + 1]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(op)[q] = u[q];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  } else {
+    // ===================== gather producers (warps 6..21) =====================
+    const int pw = warp - (2 + kEpiWarps);
+    const int rq = pw & 3;        // row quarter of the tile
+    const int quad = pw >> 2;     // deform groups quad*4 .. quad*4+3
+    const int half = quad >> 1;   // 0: groups 0..7 sample xa (flow1), 1: groups 8..15 sample xb (flow2)
+    const int row = rq * 32 + lane;
+    const uint16_t* src = a.src[half] + static_cast<long long>((quad & 1) * 4) * a.src_gstride[half];
+    const long long gstride = a.src_gstride[half], nstride = a.src_nstride[half];
+    const int pstride = a.src_pstride[half];
+    const int wps = a.W * pstride;
+    const float* fl = half ? a.flow2 : a.flow1;
+    const int H = a.H, W = a.W;
+    const float Hf = static_cast<float>(H), Wf = static_cast<float>(W);
+    // k-block of this warp inside a tap and the first 16-byte chunk it writes in each operand row
+    const int kb_in_tap = (VPG == 1) ? half : quad;
+    const int chunk0 = (VPG == 1) ? (quad & 1) * 4 : 0;
+    const uint32_t om_row = smem_u32(smem_om) + row * 96 + quad * 24;
+    const uint32_t a_row = smem_u32(smem) + row * 128;
+    const int sw = row & 7;
+    int os = 0;
+    uint32_t ophase = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int pix = tile * kTileM + row;
+      const bool valid = pix < total_pix;
+      const int n = valid ? pix / hw : 0;
+      const int off = valid ? pix - n * hw : 0;
+      const int h = off / W, w = off - h * W;
+      const float fy = valid ? __ldg(fl + (static_cast<long long>(n) * 2 + 1) * hw + off) : 0.f;
+      const float fx = valid ? __ldg(fl + (static_cast<long long>(n) * 2 + 0) * hw + off) : 0.f;
+      const uint16_t* img = src + n * nstride;
+      const int kb_base = i * kb_per_tile + kb_in_tap;
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        // ---- this tap's (dy x4 | dx x4 | mask x4) of the warp's quad
+        mbar_wait(&om_full[os], ophase);
+        const uint2 rdy = lds64(om_row + os * kOmBytes), rdx = lds64(om_row + os * kOmBytes + 8), rmk = lds64(om_row + os * kOmBytes + 16);
+        // NOTE: the slot is released at the END of the tap.  Releasing it here, right after the loads were ISSUED,
+        // lost data: nothing made the mbarrier arrive wait for the LDS results, and with 22 warps polling barriers
+        // the loads could still be queued when the TMA refill of tap+3 landed (measured: a whole warp then sampled
+        // with the offsets of tap+3).  At the end of the tap the values have been consumed by construction.
+        const int tdy = tap / 3 - 1, tdx = tap - (tap / 3) * 3 - 1;
+        const float by = static_cast<float>(h + tdy) + fy;
+        const float bx = static_cast<float>(w + tdx) + fx;
+        const int kb = kb_base + tap * a.kpt;
+        const int stage = kb % a.stages;
+        const uint32_t phase = static_cast<uint32_t>(kb / a.stages) & 1u;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t arow = a_row + static_cast<uint32_t>(stage) * a.stage_bytes;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          // the offset map is always fp16 (bf16 would quantise a 10-pixel offset to 0.04 px)
+          const float2 pdy = unpack2<false>(gi < 2 ? rdy.x : rdy.y), pdx = unpack2<false>(gi < 2 ? rdx.x : rdx.y),
+                       pmk = unpack2<false>(gi < 2 ? rmk.x : rmk.y);
+          const float sy = by + a.mrm * tanh_fast((gi & 1) ? pdy.y : pdy.x);
+          const float sx = bx + a.mrm * tanh_fast((gi & 1) ? pdx.y : pdx.x);
+          float mk = __fdividef(1.0f, 1.0f + __expf(-((gi & 1) ? pmk.y : pmk.x)));
+          // torchvision bilinear_interpolate: zero outside (-1, H) x (-1, W); corners outside the map contribute 0
+          if (!(valid && sy > -1.f && sy < Hf && sx > -1.f && sx < Wf)) mk = 0.f;
+          const float fy0 = floorf(sy), fx0 = floorf(sx);
+          const float ay = sy - fy0, ax = sx - fx0;
+          int y0 = static_cast<int>(fmaxf(fminf(fy0, Hf), -2.f)), x0 = static_cast<int>(fmaxf(fminf(fx0, Wf), -2.f));
+          const float wy0 = (y0 >= 0) ? (1.f - ay) * mk : 0.f, wy1 = (y0 + 1 <= H - 1) ? ay * mk : 0.f;
+          const float wx0 = (x0 >= 0) ? 1.f - ax : 0.f, wx1 = (x0 + 1 <= W - 1) ? ax : 0.f;
+          const float wgt[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
+          // clamped corner coordinates: a corner with zero weight may read any valid pixel
+          const int y0c = min(max(y0, 0), H - 1), y1c = min(max(y0 + 1, 0), H - 1);
+          const int x0c = min(max(x0, 0), W - 1), x1c = min(max(x0 + 1, 0), W - 1);
+          const uint16_t* gbase = img + gi * gstride;
+          const int yo0 = y0c * wps, yo1 = y1c * wps, xo0 = x0c * pstride, xo1 = x1c * pstride;
+          const int o00 = yo0 + xo0, o01 = yo0 + xo1, o10 = yo1 + xo0, o11 = yo1 + xo1;
+#pragma unroll
+          for (int vi = 0; vi < VPG; ++vi) {
+            uint4 v[4];
+            v[0] = __ldg(reinterpret_cast<const uint4*>(gbase + o00) + vi);
+            v[1] = __ldg(reinterpret_cast<const uint4*>(gbase + o01) + vi);
+            v[2] = __ldg(reinterpret_cast<const uint4*>(gbase + o10) + vi);
+            v[3] = __ldg(reinterpret_cast<const uint4*>(gbase + o11) + vi);
+            const uint4 o = blend4<BF16>(v, wgt);
+            sts128(arow + (((chunk0 + gi * VPG + vi) ^ sw) << 4), o.x, o.y, o.z, o.w);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[stage]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&om_empty[os]);
+        if (++os == kOmStages) { os = 0; ophase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(tmem_cols));
+  }
+}
+
+template <int VPG, bool BF16>
+cudaError_t launch_deform(int grid, size_t smem_bytes, cudaStream_t stream, const CUtensorMap& tmB, const CUtensorMap& tmOM,
+                          const DeformArgs& a) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(deform_conv_kernel<VPG, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return flair_launch(deform_conv_kernel<VPG, BF16>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmB, tmOM, a);
+}
+
+}  // namespace
+
+extern "C" int flair_deform_conv(const flair_deform_conv_params* p, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(p != nullptr && p->xa && p->xb && p->om && p->flow1 && p->flow2 && p->wgt && p->out,
+                "flair_deform_conv: null pointer");
+  FLAIR_REQUIRE(p->deform_groups == kGroups, "flair_deform_conv: built for 16 deform groups (got %d)", p->deform_groups);
+  FLAIR_REQUIRE(p->C == 64 || p->C == 128, "flair_deform_conv: C must be 64 or 128 (got %d); use flair_deform_im2col otherwise", p->C);
+  FLAIR_REQUIRE(p->dtype == FLAIR_F16 || p->dtype == FLAIR_BF16, "flair_deform_conv: 16-bit operands only");
+  FLAIR_REQUIRE(p->om_cstride >= 432 && p->om_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(p->om) & 15) == 0,
+                "flair_deform_conv: offset map needs >= 432 channels, stride multiple of 8, 16-byte aligned");
+  FLAIR_REQUIRE(p->out_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0, "flair_deform_conv: out alignment");
+  const int cpg = 2 * p->C / kGroups;
+  for (int s = 0; s < 2; ++s) {
+    const void* ptr = s ? p->xb : p->xa;
+    const long long gs = s ? p->xb_gstride : p->xa_gstride, ps = s ? p->xb_pstride : p->xa_pstride;
+    FLAIR_REQUIRE(static_cast<long long>(p->H) * p->W * ps < (1ll << 31), "flair_deform_conv: image too large for 32-bit offsets");
+    FLAIR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && gs % 8 == 0 && ps % 8 == 0 && ps >= cpg,
+                  "flair_deform_conv: source %d must be 16-byte aligned with strides multiple of 8", s);
+  }
+  const long long total_pix = static_cast<long long>(p->N) * p->H * p->W;
+  FLAIR_REQUIRE(total_pix > 0 && total_pix < (1ll << 31) - kTileM, "flair_deform_conv: bad extents");
+
+  DeformArgs a{};
+  a.src[0] = static_cast<const uint16_t*>(p->xa); a.src[1] = static_cast<const uint16_t*>(p->xb);
+  a.src_gstride[0] = p->xa_gstride; a.src_gstride[1] = p->xb_gstride;
+  a.src_pstride[0] = static_cast<int>(p->xa_pstride); a.src_pstride[1] = static_cast<int>(p->xb_pstride);
+  a.src_nstride[0] = p->xa_nstride; a.src_nstride[1] = p->xb_nstride;
+  a.flow1 = p->flow1; a.flow2 = p->flow2; a.bias = p->bias;
+  a.out = static_cast<uint16_t*>(p->out); a.out_cstride = p->out_cstride;
+  a.N = p->N; a.H = p->H; a.W = p->W; a.C = p->C;
+  a.kpt = 2 * p->C / kBlockK;
+  a.tiles = static_cast<int>(ceil_div_ll(total_pix, kTileM));
+  a.b_bytes = static_cast<uint32_t>(p->C) * kBlockK * 2;
+  a.stage_bytes = kABytes + a.b_bytes;
+  a.mrm = p->max_residue_magnitude;
+  a.fmt = (p->dtype == FLAIR_BF16) ? 1u : 0u;
+  const int budget = 227 * 1024 - 1024 - 512 - 1024 /*static bias*/ - kOmStages * static_cast<int>(kOmBytes);
+  int stages = budget / static_cast<int>(a.stage_bytes);
+  if (stages > 8) stages = 8;
+  FLAIR_REQUIRE(stages >= 2, "flair_deform_conv: tile does not fit shared memory");
+  a.stages = stages;
+  const size_t smem_bytes = static_cast<size_t>(stages) * a.stage_bytes + kOmStages * kOmBytes + 1024 + 512;
+
+  flair_tmap_encode_fn encode = flair_get_tmap_encode();
+  FLAIR_REQUIRE(encode != nullptr, "flair_deform_conv: cuTensorMapEncodeTiled unavailable");
+  const CUtensorMapDataType dt16 = (p->dtype == FLAIR_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tmB, tmOM;
+  {
+    // packed weight [1][C_pad16][18C] K-major (flair pack of the (C, 18C) matrix, k = tap*2C + channel)
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(18 * p->C), static_cast<cuuint64_t>(p->C)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(18 * p->C) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(p->C)};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = encode(&tmB, dt16, 2, const_cast<void*>(p->wgt), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FLAIR_REQUIRE(r == CUDA_SUCCESS, "flair_deform_conv: weight tensor map rejected (%d)", static_cast<int>(r));
+  }
+  {
+    cuuint64_t dims[2] = {432u, static_cast<cuuint64_t>(total_pix)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(p->om_cstride) * 2};
+    cuuint32_t box[2] = {48u, static_cast<cuuint32_t>(kTileM)};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = encode(&tmOM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p->om), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FLAIR_REQUIRE(r == CUDA_SUCCESS, "flair_deform_conv: offset tensor map rejected (%d)", static_cast<int>(r));
+  }
+  int grid = flair_num_sms();
+  if (grid > a.tiles) grid = a.tiles;
+  const bool bf16 = p->dtype == FLAIR_BF16;
+  cudaError_t le;
+  if (p->C == 64) le = bf16 ? launch_deform<1, true>(grid, smem_bytes, stream, tmB, tmOM, a) : launch_deform<1, false>(grid, smem_bytes, stream, tmB, tmOM, a);
+  else le = bf16 ? launch_deform<2, true>(grid, smem_bytes, stream, tmB, tmOM, a) : launch_deform<2, false>(grid, smem_bytes, stream, tmB, tmOM, a);
+  FLAIR_CHECK_CUDA(le);
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}

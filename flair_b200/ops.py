@@ -55,7 +55,7 @@ def pack_conv_weight(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
 
 
 def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, rowscale=None, residual=None, residual2=None, out=None,
-         out_dtype=None, act=L.ACT_NONE, stride=1, nchw_out=False, out_scale=1.0):
+         out_dtype=None, act=L.ACT_NONE, stride=1, nchw_out=False, out_scale=1.0, out2=None):
     """Implicit-GEMM convolution (see flair_conv_igemm in include/flair_b200.h).
 
     x: [B,T,H,W,Cin] channels-last 16-bit; wpk: pack_conv_weight(...) output."""
@@ -96,6 +96,10 @@ def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, rowscale=Non
     p.act = act
     p.in_dtype = _DT[x.dtype]
     p.out_scale = out_scale
+    if out2 is not None:  # [groups][pixels][channels per group] copy for the deformable gather
+        assert out2.dim() == 3 and out2.stride(2) == 1 and out2.stride(1) == out2.shape[2] and out2.dtype == out.dtype
+        assert out2.shape[0] * out2.shape[2] == cout and out2.shape[1] == B * T * Ho * Wo
+        p.out2 = _ptr(out2); p.out2_group_channels = out2.shape[2]; p.out2_group_stride = out2.stride(0)
     L.check(L.lib().flair_conv_igemm(C.byref(p), _stream()))
     return out
 
@@ -394,6 +398,53 @@ def deform_im2col(xa, xb, om, flow1, flow2, deform_groups, mrm):
                                         _ptr(flow1), _ptr(flow2), _ptr(cols), N, H, W, Cc, deform_groups, float(mrm),
                                         _DT[xa.dtype], _stream()))
     return cols
+
+
+def deform_offset_perm(deform_groups=16):
+    """Row permutation of the last offset-conv weight/bias that flair_deform_conv expects:
+    new channel tap*48 + quad*12 + kind*4 + gi  <-  reference channel (dy/dx: (g*9+tap)*2 + kind, mask: 288 + g*9 + tap),
+    g = quad*4 + gi."""
+    assert deform_groups == 16
+    perm = []
+    for tap in range(9):
+        for quad in range(4):
+            for kind in range(3):
+                for gi in range(4):
+                    g = quad * 4 + gi
+                    perm.append((g * 9 + tap) * 2 + kind if kind < 2 else 288 + g * 9 + tap)
+    return torch.tensor(perm, dtype=torch.long)
+
+
+def deform_conv(xa, xb, om, flow1, flow2, wpk, bias, mrm, *, out=None, group_major=False):
+    """Fused offsets + modulated deformable 3x3 conv over cat(xa, xb) (flair_deform_conv).
+
+    xa / xb: [N,H,W,C] channels-last views, or with group_major=True [8,N*H*W,C/8] planes;
+    om: [N,H,W,>=432] tap-major offset-net output (see deform_offset_perm); out: [N,H,W,C] view."""
+    N, H, W = om.shape[:3]
+    Cc = wpk.shape[1]
+    assert om.dtype == torch.float16, "the offset map is fp16 (also with bf16 features)"
+    if out is None:
+        out = torch.empty(N, H, W, Cc, dtype=wpk.dtype, device=om.device)
+    p = L.DeformConvParams()
+    for name, t in (("xa", xa), ("xb", xb)):
+        setattr(p, name, _ptr(t))
+        if group_major:
+            assert t.shape == (8, N * H * W, Cc // 8) and t.stride(2) == 1
+            gs, ps, ns = t.stride(0), t.stride(1), H * W * t.stride(1)
+        else:
+            assert t.shape == (N, H, W, Cc)
+            gs, ps, ns = Cc // 8, _cs4(t), H * W * _cs4(t)
+        setattr(p, name + "_gstride", gs); setattr(p, name + "_pstride", ps); setattr(p, name + "_nstride", ns)
+    p.om = _ptr(om); p.om_cstride = _cs4(om)
+    p.flow1 = _ptr(flow1); p.flow2 = _ptr(flow2)
+    p.wgt = _ptr(wpk); p.bias = _ptr(bias)
+    p.out = _ptr(out); p.out_cstride = _cs4(out)
+    p.N, p.H, p.W, p.C = N, H, W, Cc
+    p.deform_groups = 16
+    p.max_residue_magnitude = float(mrm)
+    p.dtype = _DT[wpk.dtype]
+    L.check(L.lib().flair_deform_conv(C.byref(p), _stream()))
+    return out
 
 
 def scale_pixels_(x, wmap):

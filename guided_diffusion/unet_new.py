@@ -366,8 +366,9 @@ class ResidualBlocksWithInputConv(nn.Module, _Packed):
         blocks = [(_w(b.conv1, dtype), _f(b.conv1.bias), _w(b.conv2, dtype), _f(b.conv2.bias)) for b in self.main[2]]
         return dict(w0=_w(self.main[0], dtype), b0=_f(self.main[0].bias), blocks=blocks)
 
-    def run(self, feat, dtype, extra_residual=None, out=None):
-        """feat: [1,N,H,W,Cin] map.  Returns main(feat) (+ extra_residual fused into the last conv)."""
+    def run(self, feat, dtype, extra_residual=None, out=None, out2=None):
+        """feat: [1,N,H,W,Cin] map.  Returns main(feat) (+ extra_residual fused into the last conv).
+        out2: optional group-major copy of the result ([groups][pixels][C/groups], flair_deform_conv's source)."""
         pk = self.packed(dtype)
         c = self.out_channels
         x = ops.conv(feat, pk["w0"], c, (1, 3, 3), bias=pk["b0"], act=L.ACT_LRELU01)
@@ -375,7 +376,7 @@ class ResidualBlocksWithInputConv(nn.Module, _Packed):
             last = i == len(pk["blocks"]) - 1
             t = ops.conv(x, w1, c, (1, 3, 3), bias=b1, act=L.ACT_RELU)
             x = ops.conv(t, w2, c, (1, 3, 3), bias=b2, residual=x, residual2=extra_residual if last else None,
-                         out=out if last else None)
+                         out=out if last else None, out2=out2 if last else None)
         return x
 
 
@@ -413,11 +414,22 @@ class SecondOrderDeformableAlignment(ModulatedDeformConv2d, _Packed):
         co = self.conv_offset
         # deformable weight (C, 2C, 3, 3) -> 1x1 GEMM weight over K = tap*2C + ci
         wd = self.weight.detach().float().permute(0, 2, 3, 1).reshape(self.out_channels, -1)
-        return dict(off=[(_w(co[i], dtype), _f(co[i].bias)) for i in (0, 2, 4, 6)],
-                    wd=ops.pack_conv_weight(wd, dtype), bd=_f(self.bias))
+        off = [(_w(co[i], dtype), _f(co[i].bias)) for i in (0, 2, 4)]
+        w6, b6 = co[6].weight.detach(), co[6].bias.detach()
+        if self.fused:  # tap-major offset channels: what flair_deform_conv stages per tap with one TMA box
+            perm = ops.deform_offset_perm(self.deform_groups).to(w6.device)
+            w6, b6 = w6[perm], b6[perm]
+        off.append((ops.pack_conv_weight(w6, dtype), b6.float().contiguous()))
+        return dict(off=off, wd=ops.pack_conv_weight(wd, dtype), bd=_f(self.bias))
 
-    def run(self, xa, xb, cond, flow_1, flow_2, dtype, out):
-        """xa/xb: [N,H,W,C] (feat_prop, feat_n2); cond: [1,N,H,W,3C+4(+pad)] offset-net input."""
+    @property
+    def fused(self):
+        """One-launch gather + tcgen05 GEMM (flair_deform_conv): the FLAIR shapes (16 deform groups, C = 64 / 128)."""
+        return self.deform_groups == 16 and self.out_channels in (64, 128)
+
+    def run(self, xa, xb, cond, flow_1, flow_2, dtype, out, xa_g=None, xb_g=None):
+        """xa/xb: [N,H,W,C] (feat_prop, feat_n2), xa_g/xb_g their group-major copies [8][N*H*W][C/8];
+        cond: [1,N,H,W,3C+4(+pad)] offset-net input."""
         pk = self.packed(dtype)
         oc = self.out_channels
         o = cond
@@ -425,6 +437,9 @@ class SecondOrderDeformableAlignment(ModulatedDeformConv2d, _Packed):
             o = ops.conv(o, w, oc, (1, 3, 3), bias=b, act=L.ACT_LRELU01)
         w, b = pk["off"][3]
         om = ops.conv(o, w, 27 * self.deform_groups, (1, 3, 3), bias=b, out_dtype=th.float16)
+        if self.fused:
+            return ops.deform_conv(xa_g, xb_g, om[0], flow_1, flow_2, pk["wd"], pk["bd"], self.max_residue_magnitude,
+                                   out=out[0], group_major=True)
         cols = ops.deform_im2col(xa, xb, om[0], flow_1, flow_2, self.deform_groups, self.max_residue_magnitude)
         return ops.conv(cols, pk["wd"], oc, (1, 1, 1), bias=pk["bd"], out=out)
 
@@ -475,6 +490,7 @@ class BasicVSRPP(nn.Module, _Packed):
             wmap = weight.reshape(T, H, W).float().contiguous()
         elif isinstance(weight, float) and weight != 1.0:
             wmap = th.full((T, H, W), weight, dtype=th.float32, device=dev)
+        wmap8 = None if wmap is None else wmap[:, None].expand(T, 8, H, W).contiguous()
         frames = hidden[0]  # [T,H,W,C]
         cpad = (3 * C + 4 + 7) // 8 * 8
         # reconstruction input for ALL frames: [spatial | backward feature | forward feature]; the two
@@ -494,7 +510,11 @@ class BasicVSRPP(nn.Module, _Packed):
             if fwd:
                 ops.copy_channels_into(rec_cat[..., C:2 * C], cat_all, C)
             ao = (2 if fwd else 1) * C
-            prop = prev2 = None
+            prop = prev2 = prop_g = prev2_g = None
+            fused = self.deform_align[name].fused
+            # group-major copies of the propagated features (written by the backbone's last conv): the layout the
+            # fused deformable conv gathers from
+            gm_all = th.empty(T, 8, H * W, C // 8, dtype=dt, device=dev) if fused else None
             for i, idx in enumerate(order):
                 aligned = cat_all[0, idx:idx + 1, :, :, ao:ao + C]  # [1,H,W,C] slice: deform output / zeros
                 if i == 0:
@@ -505,17 +525,22 @@ class BasicVSRPP(nn.Module, _Packed):
                     ops.flow_warp(prop, f1, out=cond[..., :C])
                     if i > 1:
                         ops.flow_warp(prev2, f2, out=cond[..., 2 * C:3 * C])
-                        xb = prev2
+                        xb, xb_g = prev2, prev2_g
                     else:
                         cond[..., 2 * C:3 * C].zero_()
                         xb = self._zeros(prop)
+                        xb_g = xb.view(8, H * W, C // 8)  # zeros in any layout
                     self.deform_align[name].run(prop, xb, cond[None, ..., : 3 * C + 4], f1, f2, ctx.dtype,
-                                                out=aligned[None])
+                                                out=aligned[None], xa_g=prop_g, xb_g=xb_g)
                 new = rec_cat[0, idx:idx + 1, :, :, so:so + C]
-                self.backbone[name].run(cat_all[:, idx:idx + 1], ctx.dtype, extra_residual=aligned[None], out=new[None])
+                new_g = gm_all[idx] if fused else None
+                self.backbone[name].run(cat_all[:, idx:idx + 1], ctx.dtype, extra_residual=aligned[None], out=new[None],
+                                        out2=new_g)
                 if wmap is not None:
                     ops.scale_pixels_(new, wmap[idx:idx + 1])
-                prev2, prop = prop, new
+                    if fused:
+                        ops.scale_pixels_(new_g.view(8, H, W, C // 8), wmap8[idx])
+                prev2, prop, prev2_g, prop_g = prop, new, prop_g, new_g
         # reconstruction + zero-init 1x1 + residual: not recurrent -> one batched launch chain for all frames
         pk_last = self.packed(ctx.dtype)
         rec = self.reconstruction.run(rec_cat, ctx.dtype)

@@ -96,6 +96,12 @@ typedef struct flair_conv_params {
   /* optional fused GroupNorm statistics of the OUTPUT (for the next norm):   */
   float* gn_partial;   /* NULL, or [B*T][gn_groups][2] fp32 sums, atomically  */
   int gn_groups;       /* accumulated (sum, sum of squares)                   */
+  /* optional second copy of a 16-bit NHWC output in group-major planes       */
+  /* [Cout/out2_group_channels][B*T*H*W][out2_group_channels] — the source    */
+  /* layout flair_deform_conv gathers from (BasicVSR++ feat_prop)             */
+  void* out2;
+  int out2_group_channels;       /* 8 or 16                                   */
+  long long out2_group_stride;   /* elements between group planes             */
 } flair_conv_params;
 
 int flair_conv_igemm(const flair_conv_params* p, void* stream);
@@ -284,6 +290,46 @@ int flair_deform_im2col(const void* xa, const void* xb, int xa_cstride, int xb_c
                         int dtype, void* stream);
 int flair_scale_pixels(void* x, const float* wmap, long long pixels, int C, int cstride, int dtype,
                        void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused second-order deformable alignment: offset/mask post-processing
+ * (unet_new.py:874-887; unet.py:469-482) + the whole
+ * torchvision.ops.deform_conv2d(cat(xa, xb), offset, weight, bias, padding=1,
+ * mask=mask) (unet_new.py:889-898) in ONE launch: the bilinear gather writes the
+ * tcgen05 A operand in shared memory, the im2col matrix is never materialised.
+ * C = 64 or 128, 16 deform groups (the FLAIR configurations); other shapes use
+ * flair_deform_im2col + flair_conv_igemm.
+ *
+ * Sources: element (image n, group g in 0..7, pixel (y,x), channel c in 0..C/8)
+ * of xa / xb lives at  base + n*nstride + g*gstride + (y*W + x)*pstride + c.
+ *   NHWC map [N][H][W][cstride]      : gstride = C/8, pstride = cstride
+ *   group-major planes [8][N*H*W][C/8]: gstride = N*H*W*C/8, pstride = C/8
+ * (the second is what flair_conv_igemm writes through `out2`; a warp-wide gather
+ * then touches a few cache lines instead of 32).
+ * `om`: [N*H*W][om_cstride] fp16 (always, also with bf16 features) output of the offset net with its 432 channels
+ * permuted to tap-major order: channel = tap*48 + quad*12 + kind*4 + gi for deform
+ * group quad*4 + gi, kind 0 = dy, 1 = dx, 2 = mask (reference order: dy/dx at
+ * (group*9 + tap)*2 + {0,1}, mask at 288 + group*9 + tap) — permute the rows of the
+ * last offset conv's weight/bias once at pack time.
+ * `wgt`: flair pack of the (C, 18C) matrix, k = tap*2C + channel of cat(xa, xb).
+ * ---------------------------------------------------------------------- */
+typedef struct flair_deform_conv_params {
+  const void* xa; long long xa_gstride, xa_pstride, xa_nstride;
+  const void* xb; long long xb_gstride, xb_pstride, xb_nstride;
+  const void* om; int om_cstride;
+  const float* flow1;  /* [N][2][H][W] fp32: added (flipped) to the offsets of groups 0..7  */
+  const float* flow2;  /* same for groups 8..15                                           */
+  const void* wgt;
+  const float* bias;   /* [C] or NULL                                                     */
+  void* out;           /* [N][H][W][out_cstride] 16-bit                                   */
+  int out_cstride;
+  int N, H, W, C;
+  int deform_groups;   /* 16                                                              */
+  float max_residue_magnitude;
+  int dtype;           /* FLAIR_F16 / FLAIR_BF16: sources, wgt, out (om is fp16)          */
+} flair_deform_conv_params;
+
+int flair_deform_conv(const flair_deform_conv_params* p, void* stream);
 
 #ifdef __cplusplus
 }
