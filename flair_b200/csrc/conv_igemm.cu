@@ -74,8 +74,8 @@ struct ConvKArgs {
   uint32_t fmt;
   float* gn_partial;
   int gn_groups;
-  uint16_t* out2;          // optional group-major copy of a 16-bit NHWC output: [Cout/out2_gs][pixels][out2_gs]
-  int out2_gs;
+  uint16_t* out2;          // optional copy of a 16-bit NHWC output as pair planes [Cout/out2_gs][pixels][2][out2_gs]:
+  int out2_gs;             // entry p = (pixel p, pixel p+1), the source layout of flair_deform_conv
   long long out2_gstride;  // elements between group planes
 };
 
@@ -234,9 +234,11 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_
           u.z = pack16(v[8 * q + 4], v[8 * q + 5], DT);
           u.w = pack16(v[8 * q + 6], v[8 * q + 7], DT);
           reinterpret_cast<uint4*>(op)[q] = u;
-          if (a.out2 != nullptr) {  // group-major planes for the deformable gather (flair_deform_conv)
+          if (a.out2 != nullptr) {  // pair planes for the deformable gather: slot 0 of entry pix, slot 1 of entry pix-1
             const int ch = n + 8 * q;
-            *reinterpret_cast<uint4*>(a.out2 + (ch / a.out2_gs) * a.out2_gstride + pos.pix * a.out2_gs + (ch % a.out2_gs)) = u;
+            uint16_t* e = a.out2 + (ch / a.out2_gs) * a.out2_gstride + pos.pix * (2 * a.out2_gs) + (ch % a.out2_gs);
+            *reinterpret_cast<uint4*>(e) = u;
+            if (pos.pix > 0) *reinterpret_cast<uint4*>(e - a.out2_gs) = u;
           }
         }
       } else {

@@ -41,7 +41,8 @@ constexpr int kProdWarps = 16;
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 32 * (2 + kEpiWarps + kProdWarps);  // 704
 constexpr uint32_t kABytes = kTileM * kBlockK * 2;  // 16 KB
-constexpr int kOmStages = 3;
+constexpr int kOmStages = 2;
+constexpr int kTileW = 16, kTileH = 8;
 constexpr uint32_t kOmBytes = kTileM * 48 * 2;  // one tap: 128 pixels x 48 halves
 constexpr int kGroups = 16;
 
@@ -56,7 +57,7 @@ struct DeformArgs {
   long long out_cstride;
   int N, H, W, C;
   int kpt;   // k-blocks per tap (2C / 64)
-  int tiles;
+  int tiles, tiles_x, tiles_y;  // 16 x 8-pixel tiles
   int stages;
   uint32_t b_bytes, stage_bytes;
   float mrm;
@@ -68,6 +69,24 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // Explicit shared-window accesses (32-bit addresses, STS/LDS instead of generic ST.E/LD.E).
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t x) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(x) : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ uint32_t add2(uint32_t x, uint32_t y) {
+  if (BF16) {
+    __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&x), *reinterpret_cast<__nv_bfloat162*>(&y));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __half2 r = __hadd2(*reinterpret_cast<__half2*>(&x), *reinterpret_cast<__half2*>(&y));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+// 32-byte read-only global load (LDG.E.256, sm_100+): two 16-byte vectors
+__device__ __forceinline__ void ldg256(const uint16_t* p, uint32_t (&lo)[4], uint32_t (&hi)[4]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3])
+               : "l"(p));
 }
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   uint2 v;
@@ -131,6 +150,16 @@ __device__ __forceinline__ uint4 blend4(const uint4 (&v)[4], const float (&w)[4]
   return o;
 }
 
+// tile index -> image n and top-left pixel of the 16 x 8 tile
+__device__ __forceinline__ void tile_origin(const DeformArgs& a, int tile, int& n, int& h0, int& w0) {
+  const int tx = tile % a.tiles_x;
+  const int t2 = tile / a.tiles_x;
+  const int ty = t2 % a.tiles_y;
+  n = t2 / a.tiles_y;
+  h0 = ty * kTileH;
+  w0 = tx * kTileW;
+}
+
 template <int VPG, bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
 deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOM,
@@ -192,7 +221,6 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
                            ? (a.tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
   const int kb_per_tile = 9 * a.kpt;
   const int hw = a.H * a.W;
-  const int total_pix = a.N * hw;
 
   if (warp == 0) {
     // ===================== TMA: offset rows per tap, weight slab per k-block =====================
@@ -201,11 +229,12 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
       uint32_t phase = 0, ophase = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
-        const int pix0 = tile * kTileM;
+        int tn, th0, tw0;
+        tile_origin(a, tile, tn, th0, tw0);
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&om_empty[os], ophase ^ 1);
           mbar_expect_tx(&om_full[os], kOmBytes);
-          tma_load_2d(smem_om + os * kOmBytes, &tmOM, &om_full[os], tap * 48, pix0);
+          tma_load_4d(smem_om + os * kOmBytes, &tmOM, &om_full[os], tap * 48, tw0, th0, tn);
           if (++os == kOmStages) { os = 0; ophase ^= 1; }
           for (int j = 0; j < a.kpt; ++j) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -259,8 +288,11 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int tile = blockIdx.x + local * gridDim.x;
-      const long long pix = static_cast<long long>(tile) * kTileM + row;
-      const bool valid = pix < total_pix;
+      int tn, th0, tw0;
+      tile_origin(a, tile, tn, th0, tw0);
+      const int eh = th0 + (row >> 4), ew = tw0 + (row & 15);
+      const bool valid = eh < a.H && ew < a.W;
+      const long long pix = static_cast<long long>(tn) * hw + static_cast<long long>(eh) * a.W + ew;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * n_tile) + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -291,14 +323,22 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
     }
   } else {
     // ===================== gather producers (warps 6..21) =====================
+    // Warp (rq, quad) owns tile rows rq*32..+31 (lane = pixel) x deform groups quad*4..+3: 4 samples per lane per
+    // tap.  Sources are "pair planes" [group][pixel][2][C/8]: entry p holds pixels p and p+1 of the row-major map,
+    // so the two x-corners of a bilinear sample are ONE aligned 32-byte (C = 64) / 64-byte (C = 128) load and a
+    // sample costs two L1 tag look-ups (one per row) instead of four.  The kernel is bound by L1 wavefronts
+    // (ncu: l1tex 82 % busy, L2 19 %, once the carve-out leaves L1 room for the ~36x re-read of every source
+    // pixel), so look-ups per sample are what matters; a 4-lanes-per-sample variant with shuffles had the same
+    // look-up count but 3x the instructions and as many shuffle wavefronts again.
     const int pw = warp - (2 + kEpiWarps);
     const int rq = pw & 3;        // row quarter of the tile
     const int quad = pw >> 2;     // deform groups quad*4 .. quad*4+3
     const int half = quad >> 1;   // 0: groups 0..7 sample xa (flow1), 1: groups 8..15 sample xb (flow2)
     const int row = rq * 32 + lane;
     const uint16_t* src = a.src[half] + static_cast<long long>((quad & 1) * 4) * a.src_gstride[half];
-    const long long gstride = a.src_gstride[half], nstride = a.src_nstride[half];
-    const int pstride = a.src_pstride[half];
+    const long long gstride = a.src_gstride[half];
+    const int nstride = static_cast<int>(a.src_nstride[half]);  // (< 2^31, host-checked)
+    const int pstride = a.src_pstride[half];                    // elements per pair entry = 2 * C/8
     const int wps = a.W * pstride;
     const float* fl = half ? a.flow2 : a.flow1;
     const int H = a.H, W = a.W;
@@ -313,11 +353,11 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
     uint32_t ophase = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
-      const int pix = tile * kTileM + row;
-      const bool valid = pix < total_pix;
-      const int n = valid ? pix / hw : 0;
-      const int off = valid ? pix - n * hw : 0;
-      const int h = off / W, w = off - h * W;
+      int n, th0, tw0;
+      tile_origin(a, tile, n, th0, tw0);
+      const int h = th0 + (row >> 4), w = tw0 + (row & 15);
+      const bool valid = h < H && w < W;
+      const int off = valid ? h * W + w : 0;
       const float fy = valid ? __ldg(fl + (static_cast<long long>(n) * 2 + 1) * hw + off) : 0.f;
       const float fx = valid ? __ldg(fl + (static_cast<long long>(n) * 2 + 0) * hw + off) : 0.f;
       const uint16_t* img = src + n * nstride;
@@ -329,8 +369,8 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
         const uint2 rdy = lds64(om_row + os * kOmBytes), rdx = lds64(om_row + os * kOmBytes + 8), rmk = lds64(om_row + os * kOmBytes + 16);
         // NOTE: the slot is released at the END of the tap.  Releasing it here, right after the loads were ISSUED,
         // lost data: nothing made the mbarrier arrive wait for the LDS results, and with 22 warps polling barriers
-        // the loads could still be queued when the TMA refill of tap+3 landed (measured: a whole warp then sampled
-        // with the offsets of tap+3).  At the end of the tap the values have been consumed by construction.
+        // the loads could still be queued when the TMA refill of the slot landed (measured: a whole warp then
+        // sampled with the offsets of a later tap).  At the end of the tap the values have been consumed.
         const int tdy = tap / 3 - 1, tdx = tap - (tap / 3) * 3 - 1;
         const float by = static_cast<float>(h + tdy) + fy;
         const float bx = static_cast<float>(w + tdx) + fx;
@@ -339,37 +379,56 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
         const uint32_t phase = static_cast<uint32_t>(kb / a.stages) & 1u;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         const uint32_t arow = a_row + static_cast<uint32_t>(stage) * a.stage_bytes;
+        constexpr int SB = (VPG == 1) ? 2 : 1;  // samples whose loads are in flight together (4 x 32 bytes each way)
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          // the offset map is always fp16 (bf16 would quantise a 10-pixel offset to 0.04 px)
-          const float2 pdy = unpack2<false>(gi < 2 ? rdy.x : rdy.y), pdx = unpack2<false>(gi < 2 ? rdx.x : rdx.y),
-                       pmk = unpack2<false>(gi < 2 ? rmk.x : rmk.y);
-          const float sy = by + a.mrm * tanh_fast((gi & 1) ? pdy.y : pdy.x);
-          const float sx = bx + a.mrm * tanh_fast((gi & 1) ? pdx.y : pdx.x);
-          float mk = __fdividef(1.0f, 1.0f + __expf(-((gi & 1) ? pmk.y : pmk.x)));
-          // torchvision bilinear_interpolate: zero outside (-1, H) x (-1, W); corners outside the map contribute 0
-          if (!(valid && sy > -1.f && sy < Hf && sx > -1.f && sx < Wf)) mk = 0.f;
-          const float fy0 = floorf(sy), fx0 = floorf(sx);
-          const float ay = sy - fy0, ax = sx - fx0;
-          int y0 = static_cast<int>(fmaxf(fminf(fy0, Hf), -2.f)), x0 = static_cast<int>(fmaxf(fminf(fx0, Wf), -2.f));
-          const float wy0 = (y0 >= 0) ? (1.f - ay) * mk : 0.f, wy1 = (y0 + 1 <= H - 1) ? ay * mk : 0.f;
-          const float wx0 = (x0 >= 0) ? 1.f - ax : 0.f, wx1 = (x0 + 1 <= W - 1) ? ax : 0.f;
-          const float wgt[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
-          // clamped corner coordinates: a corner with zero weight may read any valid pixel
-          const int y0c = min(max(y0, 0), H - 1), y1c = min(max(y0 + 1, 0), H - 1);
-          const int x0c = min(max(x0, 0), W - 1), x1c = min(max(x0 + 1, 0), W - 1);
-          const uint16_t* gbase = img + gi * gstride;
-          const int yo0 = y0c * wps, yo1 = y1c * wps, xo0 = x0c * pstride, xo1 = x1c * pstride;
-          const int o00 = yo0 + xo0, o01 = yo0 + xo1, o10 = yo1 + xo0, o11 = yo1 + xo1;
+        for (int g0 = 0; g0 < 4; g0 += SB) {
+          uint32_t v[SB][2][2 * VPG][4];  // [sample][row][16-byte vector: slot0 vecs, slot1 vecs][words]
+          float wgt[SB][4];               // row0*slot0, row0*slot1, row1*slot0, row1*slot1
 #pragma unroll
-          for (int vi = 0; vi < VPG; ++vi) {
-            uint4 v[4];
-            v[0] = __ldg(reinterpret_cast<const uint4*>(gbase + o00) + vi);
-            v[1] = __ldg(reinterpret_cast<const uint4*>(gbase + o01) + vi);
-            v[2] = __ldg(reinterpret_cast<const uint4*>(gbase + o10) + vi);
-            v[3] = __ldg(reinterpret_cast<const uint4*>(gbase + o11) + vi);
-            const uint4 o = blend4<BF16>(v, wgt);
-            sts128(arow + (((chunk0 + gi * VPG + vi) ^ sw) << 4), o.x, o.y, o.z, o.w);
+          for (int sgi = 0; sgi < SB; ++sgi) {
+            const int gi = g0 + sgi;
+            // the offset map is always fp16 (bf16 would quantise a 10-pixel offset to 0.04 px)
+            const float2 pdy = unpack2<false>(gi < 2 ? rdy.x : rdy.y), pdx = unpack2<false>(gi < 2 ? rdx.x : rdx.y),
+                         pmk = unpack2<false>(gi < 2 ? rmk.x : rmk.y);
+            const float sy = by + a.mrm * tanh_fast((gi & 1) ? pdy.y : pdy.x);
+            const float sx = bx + a.mrm * tanh_fast((gi & 1) ? pdx.y : pdx.x);
+            float mk = __fdividef(1.0f, 1.0f + __expf(-((gi & 1) ? pmk.y : pmk.x)));
+            // torchvision bilinear_interpolate: zero outside (-1, H) x (-1, W); corners outside the map contribute 0
+            if (!(valid && sy > -1.f && sy < Hf && sx > -1.f && sx < Wf)) mk = 0.f;
+            const float fy0 = floorf(sy), fx0 = floorf(sx);
+            const float ay = sy - fy0, ax = sx - fx0;
+            const int y0 = static_cast<int>(fmaxf(fminf(fy0, Hf), -2.f)), x0 = static_cast<int>(fmaxf(fminf(fx0, Wf), -2.f));
+            const float wy0 = (y0 >= 0) ? (1.f - ay) * mk : 0.f, wy1 = (y0 + 1 <= H - 1) ? ay * mk : 0.f;
+            // pair entry xs holds pixels (xs, xs+1).  x0 = -1: the right corner (pixel 0) is slot 0 of entry 0.
+            const float wxr = (x0 + 1 <= W - 1) ? ax : 0.f;
+            const float wxa = (x0 >= 0) ? 1.f - ax : wxr, wxb = (x0 >= 0) ? wxr : 0.f;
+            wgt[sgi][0] = wy0 * wxa; wgt[sgi][1] = wy0 * wxb; wgt[sgi][2] = wy1 * wxa; wgt[sgi][3] = wy1 * wxb;
+            // clamped coordinates: a corner with zero weight may read any valid entry
+            const int y0c = min(max(y0, 0), H - 1), y1c = min(max(y0 + 1, 0), H - 1), xs = min(max(x0, 0), W - 1);
+            const uint16_t* gbase = img + gi * gstride + xs * pstride;
+            const uint16_t* r0p = gbase + y0c * wps;
+            const uint16_t* r1p = gbase + y1c * wps;
+#pragma unroll
+            for (int q = 0; q < VPG; ++q) {  // 32 bytes per load: C = 64 -> (slot0, slot1); C = 128 -> q = slot
+              ldg256(r0p + q * 16, v[sgi][0][2 * q], v[sgi][0][2 * q + 1]);
+              ldg256(r1p + q * 16, v[sgi][1][2 * q], v[sgi][1][2 * q + 1]);
+            }
+          }
+#pragma unroll
+          for (int sgi = 0; sgi < SB; ++sgi) {
+            const int gi = g0 + sgi;
+#pragma unroll
+            for (int vi = 0; vi < VPG; ++vi) {
+              // corner vectors of output vector vi: slot s of row r = v[sgi][r][s * VPG + vi]
+              uint4 c4[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t* pv = v[sgi][c >> 1][(c & 1) * VPG + vi];
+                c4[c] = make_uint4(pv[0], pv[1], pv[2], pv[3]);
+              }
+              const uint4 o = blend4<BF16>(c4, wgt[sgi]);
+              sts128(arow + (((chunk0 + gi * VPG + vi) ^ sw) << 4), o.x, o.y, o.z, o.w);
+            }
           }
         }
         fence_proxy_async();
@@ -396,6 +455,10 @@ cudaError_t launch_deform(int grid, size_t smem_bytes, cudaStream_t stream, cons
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(deform_conv_kernel<VPG, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
     if (e != cudaSuccess) return e;
+    // ask for the smallest shared-memory carve-out that fits: the rest of the 256 KB stays L1 for the gather
+    const int pct = static_cast<int>((smem_bytes + 2048) * 100 / (228 * 1024)) + 1;
+    e = cudaFuncSetAttribute(deform_conv_kernel<VPG, BF16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+    if (e != cudaSuccess) return e;
     attr_set = true;
   }
   return flair_launch(deform_conv_kernel<VPG, BF16>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmB, tmOM, a);
@@ -417,9 +480,11 @@ extern "C" int flair_deform_conv(const flair_deform_conv_params* p, void* stream
   for (int s = 0; s < 2; ++s) {
     const void* ptr = s ? p->xb : p->xa;
     const long long gs = s ? p->xb_gstride : p->xa_gstride, ps = s ? p->xb_pstride : p->xa_pstride;
-    FLAIR_REQUIRE(static_cast<long long>(p->H) * p->W * ps < (1ll << 31), "flair_deform_conv: image too large for 32-bit offsets");
-    FLAIR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && gs % 8 == 0 && ps % 8 == 0 && ps >= cpg,
-                  "flair_deform_conv: source %d must be 16-byte aligned with strides multiple of 8", s);
+    const long long ns = s ? p->xb_nstride : p->xa_nstride;
+    FLAIR_REQUIRE(static_cast<long long>(p->H) * p->W * ps + (p->N - 1) * ns < (1ll << 31) && ns % 8 == 0,
+                  "flair_deform_conv: maps too large for 32-bit sample offsets");
+    FLAIR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && gs % 16 == 0 && ps == 2 * cpg && ns % 16 == 0,
+                  "flair_deform_conv: source %d must be 32-byte aligned pair planes (pixel stride 2 * C/8 = %d)", s, 2 * cpg);
   }
   const long long total_pix = static_cast<long long>(p->N) * p->H * p->W;
   FLAIR_REQUIRE(total_pix > 0 && total_pix < (1ll << 31) - kTileM, "flair_deform_conv: bad extents");
@@ -433,14 +498,30 @@ extern "C" int flair_deform_conv(const flair_deform_conv_params* p, void* stream
   a.out = static_cast<uint16_t*>(p->out); a.out_cstride = p->out_cstride;
   a.N = p->N; a.H = p->H; a.W = p->W; a.C = p->C;
   a.kpt = 2 * p->C / kBlockK;
-  a.tiles = static_cast<int>(ceil_div_ll(total_pix, kTileM));
+  a.tiles_x = ceil_div(p->W, kTileW); a.tiles_y = ceil_div(p->H, kTileH);
+  a.tiles = a.tiles_x * a.tiles_y * p->N;
   a.b_bytes = static_cast<uint32_t>(p->C) * kBlockK * 2;
   a.stage_bytes = kABytes + a.b_bytes;
   a.mrm = p->max_residue_magnitude;
   a.fmt = (p->dtype == FLAIR_BF16) ? 1u : 0u;
-  const int budget = 227 * 1024 - 1024 - 512 - 1024 /*static bias*/ - kOmStages * static_cast<int>(kOmBytes);
+  // Shared memory is kept to ~128 KB so that the 132 KB carve-out leaves ~120 KB of L1: the gather re-reads every
+  // source pixel ~36 times (9 taps x 4 corners) and with 16 x 8 tiles its working set is ~140 KB; with all 227 KB
+  // given to the pipeline the L1 hit rate was 5 % and the kernel ran at the L2 bandwidth limit (958 MB / launch).
+  static int smem_kb = 0;
+  if (smem_kb == 0) {
+    const char* e = getenv("FLAIR_DEFORM_SMEM_KB");
+    smem_kb = e ? atoi(e) : 128;
+    if (smem_kb < 96) smem_kb = 96;
+    if (smem_kb > 224) smem_kb = 224;
+  }
+  const int budget = smem_kb * 1024 - 1024 - 512 - 1024 /*static bias*/ - kOmStages * static_cast<int>(kOmBytes);
   int stages = budget / static_cast<int>(a.stage_bytes);
   if (stages > 8) stages = 8;
+  // The ring must hold at least one whole tap (kpt k-blocks).  The k-blocks of a tap are filled by DIFFERENT warps,
+  // which only throttle on their own stage: with fewer stages than k-blocks per tap a fast warp can be two phases
+  // ahead of the MMA on a stage, and a parity wait cannot tell "two phases ago" from "now" (it then overwrote a
+  // stage that had not been consumed: non-deterministic results at C = 128 with 3 stages).
+  if (stages < a.kpt) stages = a.kpt;
   FLAIR_REQUIRE(stages >= 2, "flair_deform_conv: tile does not fit shared memory");
   a.stages = stages;
   const size_t smem_bytes = static_cast<size_t>(stages) * a.stage_bytes + kOmStages * kOmBytes + 1024 + 512;
@@ -460,11 +541,12 @@ extern "C" int flair_deform_conv(const flair_deform_conv_params* p, void* stream
     FLAIR_REQUIRE(r == CUDA_SUCCESS, "flair_deform_conv: weight tensor map rejected (%d)", static_cast<int>(r));
   }
   {
-    cuuint64_t dims[2] = {432u, static_cast<cuuint64_t>(total_pix)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(p->om_cstride) * 2};
-    cuuint32_t box[2] = {48u, static_cast<cuuint32_t>(kTileM)};
-    cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = encode(&tmOM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p->om), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint64_t px = static_cast<cuuint64_t>(p->om_cstride) * 2;
+    cuuint64_t dims[4] = {432u, static_cast<cuuint64_t>(p->W), static_cast<cuuint64_t>(p->H), static_cast<cuuint64_t>(p->N)};
+    cuuint64_t strides[3] = {px, px * p->W, px * p->W * p->H};
+    cuuint32_t box[4] = {48u, static_cast<cuuint32_t>(kTileW), static_cast<cuuint32_t>(kTileH), 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = encode(&tmOM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(p->om), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FLAIR_REQUIRE(r == CUDA_SUCCESS, "flair_deform_conv: offset tensor map rejected (%d)", static_cast<int>(r));
   }

@@ -96,10 +96,11 @@ def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, rowscale=Non
     p.act = act
     p.in_dtype = _DT[x.dtype]
     p.out_scale = out_scale
-    if out2 is not None:  # [groups][pixels][channels per group] copy for the deformable gather
-        assert out2.dim() == 3 and out2.stride(2) == 1 and out2.stride(1) == out2.shape[2] and out2.dtype == out.dtype
-        assert out2.shape[0] * out2.shape[2] == cout and out2.shape[1] == B * T * Ho * Wo
-        p.out2 = _ptr(out2); p.out2_group_channels = out2.shape[2]; p.out2_group_stride = out2.stride(0)
+    if out2 is not None:  # pair planes [groups][pixels][2][channels per group] for the deformable gather
+        assert out2.dim() == 4 and out2.shape[2] == 2 and out2.stride(3) == 1 and out2.stride(2) == out2.shape[3] \
+            and out2.stride(1) == 2 * out2.shape[3] and out2.dtype == out.dtype
+        assert out2.shape[0] * out2.shape[3] == cout and out2.shape[1] == B * T * Ho * Wo
+        p.out2 = _ptr(out2); p.out2_group_channels = out2.shape[3]; p.out2_group_stride = out2.stride(0)
     L.check(L.lib().flair_conv_igemm(C.byref(p), _stream()))
     return out
 
@@ -415,11 +416,20 @@ def deform_offset_perm(deform_groups=16):
     return torch.tensor(perm, dtype=torch.long)
 
 
-def deform_conv(xa, xb, om, flow1, flow2, wpk, bias, mrm, *, out=None, group_major=False):
+def pair_planes(x):
+    """[N,H,W,C] channels-last map -> pair planes [8][N*H*W][2][C/8] (entry p = pixels p, p+1).  Torch ops: test /
+    setup helper; in the model the conv epilogue writes this layout directly (ops.conv(out2=...))."""
+    N, H, W, Cc = x.shape
+    g = x.reshape(N * H * W, 8, Cc // 8).permute(1, 0, 2)
+    nxt = torch.cat([g[:, 1:], torch.zeros_like(g[:, :1])], 1)
+    return torch.stack([g, nxt], 2).contiguous()
+
+
+def deform_conv(xa, xb, om, flow1, flow2, wpk, bias, mrm, *, out=None):
     """Fused offsets + modulated deformable 3x3 conv over cat(xa, xb) (flair_deform_conv).
 
-    xa / xb: [N,H,W,C] channels-last views, or with group_major=True [8,N*H*W,C/8] planes;
-    om: [N,H,W,>=432] tap-major offset-net output (see deform_offset_perm); out: [N,H,W,C] view."""
+    xa / xb: pair planes [8][N*H*W][2][C/8] (see pair_planes / ops.conv(out2=...));
+    om: [N,H,W,>=432] fp16 tap-major offset-net output (see deform_offset_perm); out: [N,H,W,C] view."""
     N, H, W = om.shape[:3]
     Cc = wpk.shape[1]
     assert om.dtype == torch.float16, "the offset map is fp16 (also with bf16 features)"
@@ -428,12 +438,9 @@ def deform_conv(xa, xb, om, flow1, flow2, wpk, bias, mrm, *, out=None, group_maj
     p = L.DeformConvParams()
     for name, t in (("xa", xa), ("xb", xb)):
         setattr(p, name, _ptr(t))
-        if group_major:
-            assert t.shape == (8, N * H * W, Cc // 8) and t.stride(2) == 1
-            gs, ps, ns = t.stride(0), t.stride(1), H * W * t.stride(1)
-        else:
-            assert t.shape == (N, H, W, Cc)
-            gs, ps, ns = Cc // 8, _cs4(t), H * W * _cs4(t)
+        assert t.shape == (8, N * H * W, 2, Cc // 8) and t.stride(3) == 1 and t.stride(2) == Cc // 8 \
+            and t.stride(1) == Cc // 4, "expected pair planes [8][N*H*W][2][C/8]"
+        gs, ps, ns = t.stride(0), t.stride(1), H * W * t.stride(1)
         setattr(p, name + "_gstride", gs); setattr(p, name + "_pstride", ps); setattr(p, name + "_nstride", ns)
     p.om = _ptr(om); p.om_cstride = _cs4(om)
     p.flow1 = _ptr(flow1); p.flow2 = _ptr(flow2)

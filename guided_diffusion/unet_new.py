@@ -368,7 +368,7 @@ class ResidualBlocksWithInputConv(nn.Module, _Packed):
 
     def run(self, feat, dtype, extra_residual=None, out=None, out2=None):
         """feat: [1,N,H,W,Cin] map.  Returns main(feat) (+ extra_residual fused into the last conv).
-        out2: optional group-major copy of the result ([groups][pixels][C/groups], flair_deform_conv's source)."""
+        out2: optional pair-plane copy of the result ([8][pixels][2][C/8], flair_deform_conv's source layout)."""
         pk = self.packed(dtype)
         c = self.out_channels
         x = ops.conv(feat, pk["w0"], c, (1, 3, 3), bias=pk["b0"], act=L.ACT_LRELU01)
@@ -428,7 +428,7 @@ class SecondOrderDeformableAlignment(ModulatedDeformConv2d, _Packed):
         return self.deform_groups == 16 and self.out_channels in (64, 128)
 
     def run(self, xa, xb, cond, flow_1, flow_2, dtype, out, xa_g=None, xb_g=None):
-        """xa/xb: [N,H,W,C] (feat_prop, feat_n2), xa_g/xb_g their group-major copies [8][N*H*W][C/8];
+        """xa/xb: [N,H,W,C] (feat_prop, feat_n2), xa_g/xb_g their pair-plane copies [8][N*H*W][2][C/8];
         cond: [1,N,H,W,3C+4(+pad)] offset-net input."""
         pk = self.packed(dtype)
         oc = self.out_channels
@@ -439,7 +439,7 @@ class SecondOrderDeformableAlignment(ModulatedDeformConv2d, _Packed):
         om = ops.conv(o, w, 27 * self.deform_groups, (1, 3, 3), bias=b, out_dtype=th.float16)
         if self.fused:
             return ops.deform_conv(xa_g, xb_g, om[0], flow_1, flow_2, pk["wd"], pk["bd"], self.max_residue_magnitude,
-                                   out=out[0], group_major=True)
+                                   out=out[0])
         cols = ops.deform_im2col(xa, xb, om[0], flow_1, flow_2, self.deform_groups, self.max_residue_magnitude)
         return ops.conv(cols, pk["wd"], oc, (1, 1, 1), bias=pk["bd"], out=out)
 
@@ -490,7 +490,10 @@ class BasicVSRPP(nn.Module, _Packed):
             wmap = weight.reshape(T, H, W).float().contiguous()
         elif isinstance(weight, float) and weight != 1.0:
             wmap = th.full((T, H, W), weight, dtype=th.float32, device=dev)
-        wmap8 = None if wmap is None else wmap[:, None].expand(T, 8, H, W).contiguous()
+        wmap8 = wmap8n = None
+        if wmap is not None:  # per-plane weight maps for the pair-plane copies (entry p: pixels p and p+1)
+            wmap8 = wmap[:, None].expand(T, 8, H, W).contiguous()
+            wmap8n = th.roll(wmap.reshape(T, H * W), -1, 1).reshape(T, 1, H, W).expand(T, 8, H, W).contiguous()
         frames = hidden[0]  # [T,H,W,C]
         cpad = (3 * C + 4 + 7) // 8 * 8
         # reconstruction input for ALL frames: [spatial | backward feature | forward feature]; the two
@@ -512,9 +515,12 @@ class BasicVSRPP(nn.Module, _Packed):
             ao = (2 if fwd else 1) * C
             prop = prev2 = prop_g = prev2_g = None
             fused = self.deform_align[name].fused
-            # group-major copies of the propagated features (written by the backbone's last conv): the layout the
-            # fused deformable conv gathers from
-            gm_all = th.empty(T, 8, H * W, C // 8, dtype=dt, device=dev) if fused else None
+            # pair-plane copies of the propagated features (written by the backbone's last conv): the layout the
+            # fused deformable conv gathers from; slot 1 of each plane's last entry is never written -> keep it finite
+            gm_all = None
+            if fused:
+                gm_all = th.empty(T, 8, H * W, 2, C // 8, dtype=dt, device=dev)
+                gm_all[:, :, -1, 1].zero_()
             for i, idx in enumerate(order):
                 aligned = cat_all[0, idx:idx + 1, :, :, ao:ao + C]  # [1,H,W,C] slice: deform output / zeros
                 if i == 0:
@@ -529,7 +535,7 @@ class BasicVSRPP(nn.Module, _Packed):
                     else:
                         cond[..., 2 * C:3 * C].zero_()
                         xb = self._zeros(prop)
-                        xb_g = xb.view(8, H * W, C // 8)  # zeros in any layout
+                        xb_g = self._zeros(gm_all[0]) if fused else None
                     self.deform_align[name].run(prop, xb, cond[None, ..., : 3 * C + 4], f1, f2, ctx.dtype,
                                                 out=aligned[None], xa_g=prop_g, xb_g=xb_g)
                 new = rec_cat[0, idx:idx + 1, :, :, so:so + C]
@@ -538,8 +544,9 @@ class BasicVSRPP(nn.Module, _Packed):
                                         out2=new_g)
                 if wmap is not None:
                     ops.scale_pixels_(new, wmap[idx:idx + 1])
-                    if fused:
-                        ops.scale_pixels_(new_g.view(8, H, W, C // 8), wmap8[idx])
+                    if fused:  # slot 0 of entry p is pixel p, slot 1 is pixel p+1
+                        ops.scale_pixels_(new_g[:, :, 0].unflatten(1, (H, W)), wmap8[idx])
+                        ops.scale_pixels_(new_g[:, :, 1].unflatten(1, (H, W)), wmap8n[idx])
                 prev2, prop, prev2_g, prop_g = prop, new, prop_g, new_g
         # reconstruction + zero-init 1x1 + residual: not recurrent -> one batched launch chain for all frames
         pk_last = self.packed(ctx.dtype)
@@ -548,11 +555,11 @@ class BasicVSRPP(nn.Module, _Packed):
                         out_dtype=stream.dtype)
 
     def _zeros(self, like):
-        z = getattr(self, "_zero_buf", None)
-        if z is None or z.shape != like.shape or z.dtype != like.dtype or z.device != like.device:
-            z = th.zeros(like.shape, dtype=like.dtype, device=like.device)
-            self._zero_buf = z
-        return z
+        bufs = self.__dict__.setdefault("_zero_bufs", {})
+        key = (tuple(like.shape), like.dtype, like.device)
+        if key not in bufs:
+            bufs[key] = th.zeros(like.shape, dtype=like.dtype, device=like.device)
+        return bufs[key]
 
 
 # --------------------------------------------------------------------------------------------------

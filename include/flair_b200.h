@@ -96,9 +96,10 @@ typedef struct flair_conv_params {
   /* optional fused GroupNorm statistics of the OUTPUT (for the next norm):   */
   float* gn_partial;   /* NULL, or [B*T][gn_groups][2] fp32 sums, atomically  */
   int gn_groups;       /* accumulated (sum, sum of squares)                   */
-  /* optional second copy of a 16-bit NHWC output in group-major planes       */
-  /* [Cout/out2_group_channels][B*T*H*W][out2_group_channels] — the source    */
-  /* layout flair_deform_conv gathers from (BasicVSR++ feat_prop)             */
+  /* optional second copy of a 16-bit NHWC output as "pair planes"            */
+  /* [Cout/gc][B*T*H*W][2][gc], gc = out2_group_channels: entry p holds pixel  */
+  /* p and pixel p+1 (row-major) — the source layout flair_deform_conv gathers */
+  /* from (BasicVSR++ feat_prop).  Slot 1 of the last entry is never written.  */
   void* out2;
   int out2_group_channels;       /* 8 or 16                                   */
   long long out2_group_stride;   /* elements between group planes             */
@@ -300,12 +301,13 @@ int flair_scale_pixels(void* x, const float* wmap, long long pixels, int C, int 
  * C = 64 or 128, 16 deform groups (the FLAIR configurations); other shapes use
  * flair_deform_im2col + flair_conv_igemm.
  *
- * Sources: element (image n, group g in 0..7, pixel (y,x), channel c in 0..C/8)
- * of xa / xb lives at  base + n*nstride + g*gstride + (y*W + x)*pstride + c.
- *   NHWC map [N][H][W][cstride]      : gstride = C/8, pstride = cstride
- *   group-major planes [8][N*H*W][C/8]: gstride = N*H*W*C/8, pstride = C/8
- * (the second is what flair_conv_igemm writes through `out2`; a warp-wide gather
- * then touches a few cache lines instead of 32).
+ * Sources are pair planes [8 groups][N*H*W entries][2][C/8] (what flair_conv_igemm
+ * writes through `out2`): entry p = (pixel p, pixel p+1) of the row-major map, so
+ * the two x-corners of a bilinear sample are one aligned 32/64-byte load.  Element
+ * (image n, group g, entry (y,x), slot s, channel c) lives at
+ *   base + n*nstride + g*gstride + (y*W + x)*pstride + s*C/8 + c,  pstride = 2*C/8.
+ * Slot 1 of the last entry of a plane must hold finite values (it is read with
+ * weight 0).
  * `om`: [N*H*W][om_cstride] fp16 (always, also with bf16 features) output of the offset net with its 432 channels
  * permuted to tap-major order: channel = tap*48 + quad*12 + kind*4 + gi for deform
  * group quad*4 + gi, kind 0 = dy, 1 = dx, 2 = mask (reference order: dy/dx at

@@ -28,10 +28,10 @@ def fwd():
     if mode == "video":
         return model(x, ts, low_res_input=clip[None], num_frames=T, enable_cross_frames=True, vsrpp_weights=1.0)
     return model(x, ts, low_res_input=clip[:, None], num_frames=1, enable_cross_frames=False)
-for _ in range(2): fwd()
+for _ in range(int(os.environ.get('NWARM', '2'))): fwd()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-n = 3
+n = int(os.environ.get('NTIMED', '3'))
 t0 = time.time(); e0.record()
 for _ in range(n): o = fwd()
 e1.record(); torch.cuda.synchronize()
