@@ -187,13 +187,9 @@ class BlurUNetOracle:
         for i in (0, 2, 4):
             o = F.leaky_relu(self.conv(o, f"{pre}.conv_offset.{i}"), 0.1)
         o = self.conv(o, pre + ".conv_offset.6")
-        o1, o2, mask = torch.chunk(o, 3, dim=1)
-        offset = mrm * torch.tanh(torch.cat((o1, o2), dim=1))
-        off1, off2 = torch.chunk(offset, 2, dim=1)
-        off1 = off1 + flow_1.flip(1).repeat(1, off1.size(1) // 2, 1, 1)
-        off2 = off2 + flow_2.flip(1).repeat(1, off2.size(1) // 2, 1, 1)
-        return torchvision.ops.deform_conv2d(x, torch.cat([off1, off2], dim=1), self.p(pre + ".weight"),
-                                             self.p(pre + ".bias"), 1, 1, 1, torch.sigmoid(mask))
+        from .kernels import deform_align_core  # (kernels imports this module: late import)
+        return deform_align_core(x[:, :x.shape[1] // 2], x[:, x.shape[1] // 2:], o, flow_1, flow_2, self.p(pre + ".weight"),
+                                 self.p(pre + ".bias"), mrm)
 
     def basicvsrpp(self, hidden, flows_forward, flows_backward, weight, pre):
         n, t, c, h, w = hidden.shape
