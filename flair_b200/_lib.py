@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
         _lib.flair_planes_to_cl.argtypes = [vp, vp, i, i, i, i, i, i, i, vp]
         _lib.flair_deform_im2col.argtypes = [vp, vp, i, i, vp, i, i, vp, vp, vp, i, i, i, i, i, f, i, vp]
         _lib.flair_scale_pixels.argtypes = [vp, vp, ll, i, i, i, vp]
+        _lib.flair_flow_warp2.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]
         _lib.flair_deform_conv.argtypes = [C.POINTER(DeformConvParams), vp]
     return _lib
 

@@ -46,6 +46,7 @@ struct ConvKArgs {
   int tmem_cols;
   int Cout, Cout_pad;
   int kblocks, ntaps, stride;
+  int k_last;  // UMMA K=16 steps that hold real channels in the LAST k-block (Cin = 196: 1 of 4)
   int stages;
   // mode 0: one (tap, k-block) per pipeline stage, A tile = 128 output pixels.
   // mode 1: "halo" — 16x8-pixel tiles; one (dt, dw, k-block) per stage loads a 16x10 halo slab of A
@@ -395,7 +396,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // One lane issues; the per-MMA instruction count is what bounds small-N tiles (a first version
+    // One ELECTED lane issues (elect.sync: the compiler then knows the region is single-threaded and emits
+    // UTCHMMA + 2 UMOV per MMA; under `if (lane == 0)` it wrapped every MMA in a 10-instruction waterfall loop).
+    // The per-MMA instruction count is what bounds small-N tiles (a first version
     // rebuilt both 64-bit descriptors and did integer div/mod per MMA: ~150 cycles per issue, tensor pipe
     // 6 % busy).  Descriptors are (constant high word, low word = smem address >> 4): the loop only adds
     // small constants to the low words.
@@ -422,17 +425,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * a.acc_cols);
       uint32_t accum = 0;  // first MMA of the tile overwrites the accumulator
       if (a.mode == 0) {
+        int kb = 0;
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          // zero-padded channels of the last k-block are skipped in whole UMMA K steps (the TMA zero fill and the
+          // zero weight columns make them no-ops; Cin = 196 / 388 would otherwise pay for 256 / 448 channels)
+          const int ksteps = (kb == a.kblocks - 1) ? a.k_last : kBlockK / kUmmaK;
+          if (++kb == a.kblocks) kb = 0;
+          if (elect_one()) {
             const uint32_t alo = desc_lo_flags | (stage0_lo + static_cast<uint32_t>(stage) * stage_step);
             const uint32_t blo = alo + a_step;
+            if (ksteps == kBlockK / kUmmaK) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // +32 B per K step inside the 128 B swizzle row (encoded >> 4)
-              umma_f16(d_tmem, desc_hi | (alo + 2u * k), desc_hi | (blo + 2u * k), idesc, accum);
-              accum = 1;
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                // +32 B per K step inside the 128 B swizzle row (encoded >> 4)
+                umma_f16(d_tmem, desc_hi | (alo + 2u * k), desc_hi | (blo + 2u * k), idesc, accum);
+                accum = 1;
+              }
+            } else {
+              for (int k = 0; k < ksteps; ++k) {
+                umma_f16(d_tmem, desc_hi | (alo + 2u * k), desc_hi | (blo + 2u * k), idesc, accum);
+                accum = 1;
+              }
             }
             umma_commit(&empty_bar[stage]);
             if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
@@ -449,7 +464,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int kb = 0; kb < a.kblocks; ++kb, ++it, wlo += b_step) {
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
-              if (lane == 0) {
+              const int ksteps = (kb == a.kblocks - 1) ? a.k_last : kBlockK / kUmmaK;
+              if (elect_one()) {
                 const uint32_t alo = desc_lo_flags | (stage0_lo + static_cast<uint32_t>(stage) * stage_step);
 #pragma unroll
                 for (int dhi = 0; dhi < 3; ++dhi) {
@@ -458,10 +474,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const uint32_t al = alo + static_cast<uint32_t>(dhi) * (2048u >> 4);
                   const uint32_t bl = resident ? wlo + static_cast<uint32_t>(dhi) * 3u * w_tap_step
                                                : alo + a_step + static_cast<uint32_t>(dhi) * b_step;
+                  if (ksteps == kBlockK / kUmmaK) {
 #pragma unroll
-                  for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    umma_f16(d_tmem, desc_hi | (al + 2u * k), desc_hi | (bl + 2u * k), idesc, accum);
-                    accum = 1;
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                      umma_f16(d_tmem, desc_hi | (al + 2u * k), desc_hi | (bl + 2u * k), idesc, accum);
+                      accum = 1;
+                    }
+                  } else {
+                    for (int k = 0; k < ksteps; ++k) {
+                      umma_f16(d_tmem, desc_hi | (al + 2u * k), desc_hi | (bl + 2u * k), idesc, accum);
+                      accum = 1;
+                    }
                   }
                 }
                 umma_commit(&empty_bar[stage]);
@@ -643,6 +666,7 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   a.acc_cols = a.tmem_cols / 2;
   a.Cout = p->Cout; a.Cout_pad = Cout_pad;
   a.kblocks = Cin_pad / kBlockK;
+  a.k_last = ceil_div(p->Cin - (a.kblocks - 1) * kBlockK, kUmmaK);
   a.stride = s;
   int nt = 0;
   for (int dt = -(p->kt / 2); dt <= p->kt / 2; ++dt)

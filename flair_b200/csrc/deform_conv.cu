@@ -265,7 +265,7 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
       for (int it = 0; it < kb_per_tile; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t alo = desc_lo_flags | (stage0_lo + static_cast<uint32_t>(stage) * stage_step);
           const uint32_t blo = alo + (kABytes >> 4);
 #pragma unroll

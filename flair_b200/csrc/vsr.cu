@@ -80,6 +80,55 @@ flow_warp_kernel(const uint16_t* __restrict__ x, const float* __restrict__ flow,
   }
 }
 
+// Two independent warps in one launch (blockIdx.y selects the pair): the first- and second-order warps of one
+// propagation step (unet_new.py:706,719) always come together, and on the serial BasicVSR++ chain a launch costs
+// more than the 8 MB it moves.
+struct Warp2Args {
+  const uint16_t* x[2];
+  const float* flow[2];
+  uint16_t* out[2];
+  int x_cstride[2];
+};
+__global__ void __launch_bounds__(256)
+flow_warp2_kernel(const __grid_constant__ Warp2Args a, int N, int H, int W, int C, int out_cstride, int dtype) {
+  pdl_sync();
+  const int s = blockIdx.y;
+  const uint16_t* __restrict__ x = a.x[s];
+  const float* __restrict__ flow = a.flow[s];
+  uint16_t* __restrict__ out = a.out[s];
+  const int x_cstride = a.x_cstride[s];
+  const int vecs = C / 8;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long items = static_cast<long long>(N) * hw * vecs;
+  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(it % vecs);
+    const long long pix = it / vecs;
+    const long long n = pix / hw;
+    const long long off = pix - n * hw;
+    const int h = static_cast<int>(off / W), w = static_cast<int>(off % W);
+    const float sx = w + __ldg(flow + (n * 2 + 0) * hw + off);
+    const float sy = h + __ldg(flow + (n * 2 + 1) * hw + off);
+    const float fx0 = floorf(sx), fy0 = floorf(sy);
+    const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
+    const float ax = sx - fx0, ay = sy - fy0;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int xx = x0 + dx, yy = y0 + dy;
+        if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+        const float wgt = (dx ? ax : 1.f - ax) * (dy ? ay : 1.f - ay);
+        float v[8];
+        ld8(x + (n * hw + static_cast<long long>(yy) * W + xx) * x_cstride + cv * 8, dtype, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, v[j], acc[j]);
+      }
+    st8(out + pix * out_cstride + cv * 8, dtype, acc);
+  }
+}
+
 // out = f1 + warp(f2, f1)   (fp32 planes [N][2][H][W]) — unet_new.py:718
 __global__ void __launch_bounds__(256)
 flow_compose_kernel(const float* __restrict__ f2, const float* __restrict__ f1, float* __restrict__ out, int N, int H,
@@ -292,6 +341,26 @@ extern "C" int flair_flow_warp(const void* x, const float* flow, void* out, int 
   FLAIR_REQUIRE(x && flow && out && C % 8 == 0 && x_cstride % 8 == 0 && out_cstride % 8 == 0, "flair_flow_warp: bad arguments");
   FLAIR_CHECK_CUDA(flair_launch(flow_warp_kernel, dim3(blocks_for(static_cast<long long>(N) * H * W * (C / 8))), dim3(256), 0, stream, 
       static_cast<const uint16_t*>(x), flow, static_cast<uint16_t*>(out), N, H, W, C, x_cstride, out_cstride, dtype));
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int flair_flow_warp2(const void* xa, const void* xb, const float* flow_a, const float* flow_b, void* out_a,
+                                void* out_b, int N, int H, int W, int C, int xa_cstride, int xb_cstride, int out_cstride,
+                                int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(xa && xb && flow_a && flow_b && out_a && out_b && C % 8 == 0 && xa_cstride % 8 == 0 && xb_cstride % 8 == 0 &&
+                    out_cstride % 8 == 0,
+                "flair_flow_warp2: bad arguments");
+  Warp2Args a;
+  a.x[0] = static_cast<const uint16_t*>(xa); a.x[1] = static_cast<const uint16_t*>(xb);
+  a.flow[0] = flow_a; a.flow[1] = flow_b;
+  a.out[0] = static_cast<uint16_t*>(out_a); a.out[1] = static_cast<uint16_t*>(out_b);
+  a.x_cstride[0] = xa_cstride; a.x_cstride[1] = xb_cstride;
+  const long long items = static_cast<long long>(N) * H * W * (C / 8);
+  int bx = blocks_for(items) / 2;
+  if (bx < 1) bx = 1;
+  FLAIR_CHECK_CUDA(flair_launch(flow_warp2_kernel, dim3(bx, 2), dim3(256), 0, stream, a, N, H, W, C, out_cstride, dtype));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }

@@ -380,6 +380,14 @@ def flow_warp(x, flow, out=None):
     return out
 
 
+def flow_warp2(xa, flow_a, out_a, xb, flow_b, out_b):
+    """out_a = warp(xa, flow_a), out_b = warp(xb, flow_b) in one launch (same shapes, same output channel stride)."""
+    N, H, W, Cc = xa.shape
+    assert xb.shape == xa.shape and _cs4(out_a) == _cs4(out_b)
+    L.check(L.lib().flair_flow_warp2(_ptr(xa), _ptr(xb), _ptr(flow_a), _ptr(flow_b), _ptr(out_a), _ptr(out_b), N, H, W, Cc,
+                                     _cs4(xa), _cs4(xb), _cs4(out_a), _DT[xa.dtype], _stream()))
+
+
 def flow_compose(f2, f1):
     out = torch.empty_like(f1)
     N, _, H, W = f1.shape

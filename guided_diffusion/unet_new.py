@@ -528,11 +528,11 @@ class BasicVSRPP(nn.Module, _Packed):
                 else:
                     cond = cond_all[0, idx:idx + 1]
                     f1, f2 = f12[name][idx:idx + 1, 0:2], f12[name][idx:idx + 1, 2:4]
-                    ops.flow_warp(prop, f1, out=cond[..., :C])
                     if i > 1:
-                        ops.flow_warp(prev2, f2, out=cond[..., 2 * C:3 * C])
+                        ops.flow_warp2(prop, f1, cond[..., :C], prev2, f2, cond[..., 2 * C:3 * C])
                         xb, xb_g = prev2, prev2_g
                     else:
+                        ops.flow_warp(prop, f1, out=cond[..., :C])
                         cond[..., 2 * C:3 * C].zero_()
                         xb = self._zeros(prop)
                         xb_g = self._zeros(gm_all[0]) if fused else None

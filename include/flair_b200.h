@@ -282,6 +282,9 @@ int flair_pack_im2col6(const float* a, const float* b, void* out, int N, int H, 
  * ---------------------------------------------------------------------- */
 int flair_flow_warp(const void* x, const float* flow, void* out, int N, int H, int W, int C,
                     int x_cstride, int out_cstride, int dtype, void* stream);
+/* the first- and second-order warps of one propagation step (unet_new.py:706,719) in one launch */
+int flair_flow_warp2(const void* xa, const void* xb, const float* flow_a, const float* flow_b, void* out_a, void* out_b,
+                     int N, int H, int W, int C, int xa_cstride, int xb_cstride, int out_cstride, int dtype, void* stream);
 int flair_flow_compose_f32(const float* f2, const float* f1, float* out, int N, int H, int W, void* stream);
 int flair_planes_to_cl(const float* src, void* dst, int N, int Cs, int H, int W, int dst_cstride,
                        int dst_coffset, int dtype, void* stream);
