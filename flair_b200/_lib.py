@@ -94,7 +94,7 @@ def lib() -> C.CDLL:
         _lib.flair_jpeg_f32.argtypes = [i, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, vp]
         _lib.flair_sandwich_f32.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp]
         _lib.flair_gn_stats_chunks.argtypes = [ll, i]
-        _lib.flair_gn_stats.argtypes = [vp, i, i, ll, i, i, i, vp, i, vp]
+        _lib.flair_gn_stats.argtypes = [vp, i, i, ll, i, i, i, vp, i, vp, vp, f, vp]
         _lib.flair_gn_apply.argtypes = [C.POINTER(GNApplyParams), vp]
         _lib.flair_copy_channels.argtypes = [vp, vp, ll, i, i, i, i, i, vp]
         _lib.flair_attn_spatial.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, vp]

@@ -9,6 +9,8 @@
 // the reference spends >= 3 fp32 passes per norm (cast, native_group_norm, SiLU, cast).
 //
 // Layout: x[b][p][c], p = (t,h,w) pixel index, c fastest.  Group g owns channels [g*cpg,(g+1)*cpg).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/flair_b200.h"
 
@@ -58,11 +60,27 @@ __device__ __forceinline__ void store8(void* base, long long elem_off, int dtype
   }
 }
 
+__device__ __forceinline__ void unpack8(const uint4& u, int dtype, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f;
+    if (dtype == FLAIR_F16) {
+      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      f = __half22float2(h);
+    } else {
+      f = unpack_bf16x2(w[i]);
+    }
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+
 // ---------------------------------------------------------------- statistics (partial sums)
 // grid (nchunks, B); block = vecs * ppb threads (vecs = C/8).  partial[b][chunk][g] = (sum, sumsq).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 gn_stats_kernel(const void* __restrict__ x, int dtype, long long P, int C, int cstride, int groups,
-                int ppb, long long pix_per_chunk, float2* __restrict__ partial) {
+                int ppb, long long pix_per_chunk, float2* __restrict__ partial, int* __restrict__ counter,
+                float2* __restrict__ final_stats, float eps) {
   pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   extern __shared__ float sm[];  // [2][ppb][C]
   const int vecs = C / 8;
@@ -75,7 +93,32 @@ gn_stats_kernel(const void* __restrict__ x, int dtype, long long P, int C, int c
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
   const long long base = static_cast<long long>(b) * P;
-  for (long long p = p0 + pl; p < p1; p += ppb) {
+  // 8 independent 16-byte loads in flight per thread (one per iteration kept ~8 KB in flight per SM: 1.7 TB/s);
+  // the accumulation order per thread is unchanged, so the statistics are bit-identical to the simple loop
+  // (ncu: with 2 resident CTAs x 8 loads DRAM was 23 % busy and nothing else above 16 %: latency-bound.  The loads
+  // are kept as raw 16-byte registers until consumed so that 4 CTAs fit per SM: 32 warps x 8 x 512 B in flight.)
+  constexpr int kU = 8;
+  long long p = p0 + pl;
+  if (dtype != FLAIR_F32) {
+    const uint16_t* xp = static_cast<const uint16_t*>(x);
+    for (; p < p1; p += static_cast<long long>(kU) * ppb) {  // predicated batches, same accumulation order
+      uint4 raw[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (p + static_cast<long long>(u) * ppb < p1)
+          raw[u] = __ldg(reinterpret_cast<const uint4*>(xp + (base + p + static_cast<long long>(u) * ppb) * cstride + cv * 8));
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (p + static_cast<long long>(u) * ppb < p1) {
+          float v[8];
+          unpack8(raw[u], dtype, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+        }
+      }
+    }
+  }
+  for (; p < p1; p += ppb) {
     float v[8];
     load8(x, (base + p) * cstride + cv * 8, dtype, v);
 #pragma unroll
@@ -102,6 +145,43 @@ gn_stats_kernel(const void* __restrict__ x, int dtype, long long P, int C, int c
     for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { a += sS[c]; d += sQ[c]; }
     partial[(static_cast<long long>(b) * gridDim.x + chunk) * groups + threadIdx.x] = make_float2(a, d);
   }
+  if (counter == nullptr) return;
+  // ---- the LAST chunk of this batch element to finish reduces all partials once, in chunk order (deterministic),
+  // and writes (mean, rstd): the apply kernels then read 2 floats per group instead of every CTA re-reducing
+  // ~300 partials in its prologue (that prologue was 10-20 us of a 25-60 us apply launch).
+  __shared__ int s_last;
+  __shared__ double s_red[2][8][kGroupsMax];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter + b, 1) == static_cast<int>(gridDim.x) - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nch = gridDim.x;
+  // 8 slots per group, each a contiguous range of chunks; combined in slot order (blockDim may be < 8 * groups)
+  for (int idx = threadIdx.x; idx < 8 * groups; idx += blockDim.x) {
+    const int g = idx % groups, part = idx / groups;
+    const int per = (nch + 7) / 8;
+    const int k0 = part * per, k1 = min(nch, k0 + per);
+    double sd = 0.0, qd = 0.0;
+    for (int k = k0; k < k1; ++k) {
+      const float2 v = __ldcg(partial + (static_cast<long long>(b) * nch + k) * groups + g);
+      sd += v.x; qd += v.y;
+    }
+    s_red[0][part][g] = sd; s_red[1][part][g] = qd;
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    double sd = 0.0, qd = 0.0;
+    for (int part = 0; part < 8; ++part) { sd += s_red[0][part][threadIdx.x]; qd += s_red[1][part][threadIdx.x]; }
+    const double n = static_cast<double>(P) * (C / groups);
+    const double mean = sd / n;
+    double var = qd / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    final_stats[static_cast<long long>(b) * groups + threadIdx.x] =
+        make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+  }
+  if (threadIdx.x == 0) counter[b] = 0;  // self-cleaning: the next launch on this stream finds zeros
 }
 
 struct ApplyArgs {
@@ -122,7 +202,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ A
   __shared__ float s_mean[kGroupsMax], s_rstd[kGroupsMax];
   const int b = blockIdx.y;
   const int cpg = a.C / a.groups;
-  if (a.norm && threadIdx.x < a.groups) {
+  if (a.norm && a.nchunks == 0 && threadIdx.x < a.groups) {  // statistics already finalised by gn_stats
+    const float2 v = __ldg(a.partial + static_cast<long long>(b) * a.groups + threadIdx.x);
+    s_mean[threadIdx.x] = v.x;
+    s_rstd[threadIdx.x] = v.y;
+  } else if (a.norm && threadIdx.x < a.groups) {
     double s = 0.0, q = 0.0;
     for (int k = 0; k < a.nchunks; ++k) {
       const float2 v = __ldg(a.partial + (static_cast<long long>(b) * a.nchunks + k) * a.groups + threadIdx.x);
@@ -221,13 +305,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ A
 // keeps one 8-channel vector, so the whole per-channel affine (statistics, gamma/beta, FiLM) folds into
 // y = x * A + B held in registers; the inner loop is one 16-byte load, 8 FMAs (+ SiLU), one 16-byte store.
 // grid (blocks, B*T)
-__global__ void __launch_bounds__(256) gn_apply_fast_kernel(const __grid_constant__ ApplyArgs a) {
+__global__ void __launch_bounds__(256, 3) gn_apply_fast_kernel(const __grid_constant__ ApplyArgs a) {
   pdl_sync();
   __shared__ float s_mean[kGroupsMax], s_rstd[kGroupsMax];
   const int frame = blockIdx.y;  // b*T + t
   const int b = frame / a.T;
   const int cpg = a.C / a.groups;
-  if (a.norm && threadIdx.x < a.groups) {
+  if (a.norm && a.nchunks == 0 && threadIdx.x < a.groups) {  // statistics already finalised by gn_stats
+    const float2 v = __ldg(a.partial + static_cast<long long>(b) * a.groups + threadIdx.x);
+    s_mean[threadIdx.x] = v.x;
+    s_rstd[threadIdx.x] = v.y;
+  } else if (a.norm && threadIdx.x < a.groups) {
     double s = 0.0, q = 0.0;
     for (int k = 0; k < a.nchunks; ++k) {
       const float2 v = __ldg(a.partial + (static_cast<long long>(b) * a.nchunks + k) * a.groups + threadIdx.x);
@@ -246,33 +334,82 @@ __global__ void __launch_bounds__(256) gn_apply_fast_kernel(const __grid_constan
   const int c0 = cv * 8;
   float A[8], Bc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float ga = 1.0f, be = 0.0f;
-    if (a.norm) {
+  for (int j = 0; j < 8; ++j) { A[j] = 1.0f; Bc[j] = 0.0f; }
+  if (a.norm) {
+    // per-channel constants with 16-byte loads (they were 32 scalar loads per thread: on the small maps this
+    // prologue cost more than the pixels)
+    float ga[8], be[8];
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(a.beta + c0) + 1);
+    ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+    be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
       const int grp = (c0 + j) / cpg;
-      const float g = __ldg(a.gamma + c0 + j) * s_rstd[grp];
-      ga = g;
-      be = __ldg(a.beta + c0 + j) - s_mean[grp] * g;
-      if (a.scale != nullptr) {
-        const long long row = static_cast<long long>(frame) * a.film_stride;
-        const float sc = 1.0f + __ldg(a.scale + row + c0 + j);
-        ga *= sc;
-        be = be * sc + __ldg(a.shift + row + c0 + j);
+      const float g = ga[j] * s_rstd[grp];
+      A[j] = g;
+      Bc[j] = be[j] - s_mean[grp] * g;
+    }
+    if (a.scale != nullptr) {
+      const long long row = static_cast<long long>(frame) * a.film_stride + c0;
+      float sc[8], sh[8];
+      if ((a.film_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(a.scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.shift) & 15) == 0) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.scale + row)), s1 = __ldg(reinterpret_cast<const float4*>(a.scale + row) + 1);
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(a.shift + row)), h1 = __ldg(reinterpret_cast<const float4*>(a.shift + row) + 1);
+        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+        sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = __ldg(a.scale + row + j); sh[j] = __ldg(a.shift + row + j); }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float m = 1.0f + sc[j];
+        A[j] *= m;
+        Bc[j] = Bc[j] * m + sh[j];
       }
     }
-    A[j] = ga; Bc[j] = be;
   }
   const long long P = static_cast<long long>(a.H) * a.W;
   const long long base = static_cast<long long>(frame) * P;
-  for (long long p = static_cast<long long>(blockIdx.x) * ppb + pl; p < P; p += static_cast<long long>(gridDim.x) * ppb) {
-    float v[8];
-    load8(a.x, (base + p) * a.x_cstride + c0, a.in_dtype, v);
+  const long long stride = static_cast<long long>(gridDim.x) * ppb;
+  auto xform = [&](float (&v)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float y = fmaf(v[j], A[j], Bc[j]);
-      if (a.silu) y = silu_f(y);
+      if (a.silu) {  // y * sigmoid(y) = h + h * tanh(h), h = y/2: ONE MUFU op (tanh.approx, rel. error 2^-11) instead of ex2 + rcp
+        const float h = 0.5f * y;
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+        y = fmaf(h, t, h);
+      }
       v[j] = y;
     }
+  };
+  constexpr int kU = 8;  // independent 16-byte loads in flight per thread, kept raw until consumed (register budget)
+  long long p = static_cast<long long>(blockIdx.x) * ppb + pl;
+  if (a.in_dtype != FLAIR_F32) {
+    const uint16_t* xp = static_cast<const uint16_t*>(a.x);
+    for (; p < P; p += kU * stride) {  // predicated batches: no scalar tail (it ran with one load in flight)
+      uint4 raw[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (p + u * stride < P) raw[u] = __ldg(reinterpret_cast<const uint4*>(xp + (base + p + u * stride) * a.x_cstride + c0));
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (p + u * stride < P) {
+          float v[8];
+          unpack8(raw[u], a.in_dtype, v);
+          xform(v);
+          store8(a.out, (base + p + u * stride) * a.out_cstride + c0, a.out_dtype, v);
+        }
+      }
+    }
+  }
+  for (; p < P; p += stride) {
+    float v[8];
+    load8(a.x, (base + p) * a.x_cstride + c0, a.in_dtype, v);
+    xform(v);
     store8(a.out, (base + p) * a.out_cstride + c0, a.out_dtype, v);
   }
 }
@@ -309,18 +446,25 @@ extern "C" int flair_gn_stats_chunks(long long pixels_per_batch, int C) {
   if (ppb > 32) ppb = 32;
   long long chunks = pixels_per_batch / (static_cast<long long>(ppb) * 16);
   if (chunks < 1) chunks = 1;
-  if (chunks > 296) chunks = 296;
+  static int cap = 0;
+  if (cap == 0) {
+    const char* e = getenv("FLAIR_GN_CHUNKS");
+    cap = e ? atoi(e) : 296;
+    if (cap < 1) cap = 296;
+  }
+  if (chunks > cap) chunks = cap;
   return static_cast<int>(chunks);
 }
 
 extern "C" int flair_gn_stats(const void* x, int dtype, int B, long long P, int C, int cstride, int groups,
-                              float* partial, int nchunks, void* stream_) {
+                              float* partial, int nchunks, int* counter, float* final_stats, float eps, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FLAIR_REQUIRE(x && partial, "flair_gn_stats: null pointer");
   FLAIR_REQUIRE(groups > 0 && groups <= kGroupsMax && C % groups == 0 && C % 8 == 0 && C <= 2048,
                 "flair_gn_stats: unsupported C=%d groups=%d", C, groups);
   FLAIR_REQUIRE(cstride % 8 == 0 && cstride >= C, "flair_gn_stats: bad channel stride %d", cstride);
   FLAIR_REQUIRE(nchunks > 0 && B > 0 && B < 65536, "flair_gn_stats: bad grid");
+  FLAIR_REQUIRE((counter == nullptr) == (final_stats == nullptr), "flair_gn_stats: counter and final_stats go together");
   const int vecs = C / 8;
   int ppb = 256 / vecs;
   if (ppb < 1) ppb = 1;
@@ -329,7 +473,8 @@ extern "C" int flair_gn_stats(const void* x, int dtype, int B, long long P, int 
   const size_t smem = sizeof(float) * 2 * ppb * C;
   dim3 grid(nchunks, B);
   FLAIR_CHECK_CUDA(flair_launch(gn_stats_kernel, dim3(grid), dim3(vecs * ppb), smem, stream, x, dtype, P, C, cstride, groups, ppb, ppc,
-                                                     reinterpret_cast<float2*>(partial)));
+                                reinterpret_cast<float2*>(partial), counter, reinterpret_cast<float2*>(final_stats),
+                                eps > 0 ? eps : 1e-5f));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }
@@ -340,7 +485,7 @@ extern "C" int flair_gn_apply(const flair_gn_apply_params* p, void* stream_) {
   FLAIR_REQUIRE(p->C % 8 == 0 && p->x_cstride % 8 == 0 && p->out_cstride % 8 == 0, "flair_gn_apply: C must be a multiple of 8");
   if (p->norm)
     FLAIR_REQUIRE(p->partial && p->gamma && p->beta && p->groups > 0 && p->groups <= kGroupsMax &&
-                      p->C % p->groups == 0 && p->nchunks > 0,
+                      p->C % p->groups == 0 && p->nchunks >= 0,
                   "flair_gn_apply: bad normalisation arguments");
   FLAIR_REQUIRE(p->resample >= 0 && p->resample <= 2, "flair_gn_apply: resample must be 0, 1 or 2");
   if (p->resample == 2) FLAIR_REQUIRE(p->H % 2 == 0 && p->W % 2 == 0, "flair_gn_apply: odd size for 2x2 pooling");
@@ -356,8 +501,8 @@ extern "C" int flair_gn_apply(const flair_gn_apply_params* p, void* stream_) {
     const long long P = static_cast<long long>(p->H) * p->W;
     const int ppb = 256 / vecs_;
     const int frames = p->B * p->T;
-    long long bx = ceil_div_ll(P, static_cast<long long>(ppb) * 4);  // >= 4 pixels per thread
-    const long long cap = ceil_div_ll(static_cast<long long>(flair_num_sms()) * 8, frames);
+    long long bx = ceil_div_ll(P, static_cast<long long>(ppb) * 16);  // >= 16 pixels per thread (prologue amortised)
+    const long long cap = ceil_div_ll(static_cast<long long>(flair_num_sms()) * 3, frames);  // one wave of 3 CTAs per SM
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     FLAIR_CHECK_CUDA(flair_launch(gn_apply_fast_kernel, dim3(static_cast<unsigned>(bx), frames), dim3(256), 0, stream, a));

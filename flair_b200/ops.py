@@ -265,14 +265,32 @@ def sandwich(Lm, X, Rm, sub=None):
 # ----------------------------------------------------------------------------------------------
 # UNet building blocks on channels-last [B,T,H,W,C] maps
 # ----------------------------------------------------------------------------------------------
-def gn_stats(x, groups=32):
-    """Partial GroupNorm sums over (T,H,W,C/G) per batch element: returns (partial, nchunks)."""
+_GN_COUNTERS = {}
+
+
+def _gn_counter(device, B):
+    """Zeroed ticket counters of flair_gn_stats (self-cleaning; one buffer per device and stream, allocated on the
+    first eager call, i.e. before any CUDA-graph capture)."""
+    key = (device, _stream())
+    c = _GN_COUNTERS.get(key)
+    if c is None or c.numel() < B:
+        c = torch.zeros(max(B, 64), dtype=torch.int32, device=device)
+        _GN_COUNTERS[key] = c
+    return c
+
+
+def gn_stats(x, groups=32, eps=1e-5):
+    """GroupNorm statistics over (T,H,W,C/G) per batch element.  Returns (final, 0): final[b][g] = (mean, rstd),
+    reduced deterministically by the last CTA of the launch (see flair_gn_stats); gn_apply takes the pair as is."""
     B, T, H, W, Cc = x.shape
     P = T * H * W
     n = L.lib().flair_gn_stats_chunks(P, Cc)
-    partial = torch.empty(B, n, groups, 2, dtype=torch.float32, device=x.device)
-    L.check(L.lib().flair_gn_stats(_ptr(x), _DT[x.dtype], B, P, Cc, _cstride(x), groups, _ptr(partial), n, _stream()))
-    return partial, n
+    counter = _gn_counter(x.device, B)
+    part = torch.empty(B, n, groups, 2, dtype=torch.float32, device=x.device)
+    fin = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
+    L.check(L.lib().flair_gn_stats(_ptr(x), _DT[x.dtype], B, P, Cc, _cstride(x), groups, _ptr(part), n,
+                                   _ptr(counter), _ptr(fin), float(eps), _stream()))
+    return fin, 0
 
 
 def gn_apply(x, stats=None, gamma=None, beta=None, *, scale=None, shift=None, silu=False, resample=0,

@@ -213,14 +213,19 @@ int flair_sandwich_f32(const float* L, const float* X, const float* Rm, const fl
  * (statistics over (C/G,T,H,W) per batch element), the SiLU that follows,
  * the scale-shift conditioning (unet_new.py:321-325) and the 2x resampling of
  * up/down ResBlocks (unet_new.py:249-254,310-315).
- *   flair_gn_stats: partial[b][chunk][g] = (sum, sum of squares), fp32
- *   flair_gn_apply: finishes the statistics and writes
+ *   flair_gn_stats: partial[b][chunk][g] = (sum, sum of squares), fp32.  With `counter`
+ *        (device int[B], zero before the first use, left zero) and `final_stats` the last
+ *        chunk to finish also writes final_stats[b][g] = (mean, rstd), reduced in chunk
+ *        order in double (deterministic); launches sharing a counter must be stream-ordered.
+ *   flair_gn_apply: finishes the statistics (nchunks > 0: `partial` = the partial sums;
+ *        nchunks == 0: `partial` = final_stats) and writes
  *        out = resample( silu?( ((x-mean)*rstd*gamma+beta) * (1+scale) + shift ) )
  *   (norm = 0 skips the normalisation: plain resample / dtype cast of x).
  * ---------------------------------------------------------------------- */
 int flair_gn_stats_chunks(long long pixels_per_batch, int C);
 int flair_gn_stats(const void* x, int dtype, int B, long long pixels_per_batch, int C, int cstride,
-                   int groups, float* partial, int nchunks, void* stream);
+                   int groups, float* partial, int nchunks, int* counter, float* final_stats, float eps,
+                   void* stream);
 typedef struct flair_gn_apply_params {
   const void* x; int in_dtype;   /* [B][T][H][W][x_cstride]                   */
   void* out; int out_dtype;      /* [B][T][H'][W'][out_cstride]               */
