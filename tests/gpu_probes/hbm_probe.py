@@ -46,26 +46,24 @@ for (T, H, C) in ((10, 256, 64), (10, 128, 128), (10, 64, 256)):
     stats = [ops.gn_stats(x) for x in xs]
     report(f"gn_stats   [1,{T},{H},{H},{C}] fp16", timeit([lambda x=x: ops.gn_stats(x) for x in xs]), n * 2)
     report(f"gn_apply+FiLM+SiLU [1,{T},{H},{H},{C}] fp16", timeit([lambda x=x, s=s, o=o: ops.gn_apply(x, s, gamma, beta, scale=film[:, :C], shift=film[:, C:], silu=True, out=o) for x, s, o in zip(xs, stats, outs)]), n * 4)
-# ---- fused sampler update + blur data consistency, 64 frames per launch
+# ---- sampler tail at 64 frames per launch: pred_xstart -> Down -> InvhTh -> fused update (blur DC in-register)
 N, S = 64, 256
 diffusion = pipeline.make_diffusion("gaussian")
 kern = np.load("flair_b200/data/blur_kernel_k03.npy")
 A = pipeline.make_operator("gaussian", torch.device(dev), S, kernels_mat=kern)
-hr = synth.synthetic_clip(N, S, seed=1).to(dev) * 2 - 1
-y = A.DownscaleOP(hr)
-restore = pipeline.BlurRestore(A, y)
-sets = []
-for _ in range(R):
-    sets.append(dict(x=torch.randn(N, 3, S, S, device=dev), mo=torch.randn(N, 6, S, S, device=dev), z=torch.randn(N, 3, S, S, device=dev)))
+coef = diffusion._table(torch.device(dev), "update")
 t = torch.full((N,), 50, device=dev, dtype=torch.long)
 gam = torch.full((N,), 0.5, device=dev)
-def step(d):
-    return diffusion.p_sample(lambda *a, **k: d["mo"], d["x"], t, model_kwargs={}, restore_fn=restore, rho=0.25, gamma=gam, _noise=d["z"])
-try:
-    us = timeit([lambda d=d: step(d) for d in sets], reps=3)
-    report(f"p_sample tail (x0, blur DC, update) {N} frames 256^2", us, N * 3.93e6)
-except Exception as e:
-    print("p_sample probe failed:", repr(e)[:200])
-# ---- stand-alone blur restore (G2) and jpeg codec
-xs = [torch.randn(N, 3, S, S, device=dev) for _ in range(R)]
-report(f"A_pinv blur restore R(x) {N} frames 256^2", timeit([lambda x=x: restore(x) for x in xs], reps=3), N * 1.62e6)
+taps_ds = A.DownscaleOP.Filter_OP.taps
+taps_inv = A.Conv_LR_with_Inv_hTh_OP.Filter_OP.taps
+taps_up = A.Upscale_OP.Filter_OP.taps
+sf, pre = int(A.ds_factor), int(A.pre_stride[0])
+sets = [dict(x=torch.randn(N, 3, S, S, device=dev), mo=torch.randn(N, 6, S, S, device=dev), z=torch.randn(N, 3, S, S, device=dev),
+             x0=torch.randn(N, 3, S, S, device=dev).clamp(-1, 1), lr=torch.randn(N, 3, S // 4, S // 4, device=dev),
+             sub=torch.randn(N, 3, S // 4, S // 4, device=dev)) for _ in range(R)]
+plane = N * 3 * S * S * 4
+report(f"pred_xstart (read x_t, eps; write x0) {N} frames", timeit([lambda d=d: ops.pred_xstart(d["x"], d["mo"], coef, t_arr=t) for d in sets]), 3 * plane)
+report(f"blur_down 9x9 /4 (read x0; write LR) {N} frames", timeit([lambda d=d: ops.blur_down(d["x0"], taps_ds, sf, pre) for d in sets]), plane + plane // 16)
+report(f"filter_same 39x39 on LR (read, sub; write) {N} frames", timeit([lambda d=d: ops.filter_same(d["lr"], taps_inv, sub=d["sub"]) for d in sets]), 3 * plane // 16)
+report(f"sampler_update + in-register Up(q) (3.93 MB/frame) {N} fr", timeit([lambda d=d: ops.sampler_update(d["x"], coef, model_out=d["mo"], noise=d["z"], t_arr=t, gamma_arr=gam, q_lr=d["lr"], up_taps=taps_up, sf=sf, pre_stride=pre, rho=0.25) for d in sets]), N * 3.93e6)
+report(f"sampler_update, no DC (3.15 MB/frame + x0) {N} frames", timeit([lambda d=d: ops.sampler_update(d["x"], coef, model_out=d["mo"], noise=d["z"], t_arr=t, rho=0.25) for d in sets]), 5 * plane)
