@@ -164,9 +164,13 @@ gn_stats_kernel(const void* __restrict__ x, int dtype, long long P, int C, int c
     const int per = (nch + 7) / 8;
     const int k0 = part * per, k1 = min(nch, k0 + per);
     double sd = 0.0, qd = 0.0;
-    for (int k = k0; k < k1; ++k) {
-      const float2 v = __ldcg(partial + (static_cast<long long>(b) * nch + k) * groups + g);
-      sd += v.x; qd += v.y;
+    for (int k = k0; k < k1; k += 8) {  // 8 loads in flight, summed in chunk order
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = (k + u < k1) ? __ldcg(partial + (static_cast<long long>(b) * nch + k + u) * groups + g) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { sd += v[u].x; qd += v[u].y; }
     }
     s_red[0][part][g] = sd; s_red[1][part][g] = qd;
   }

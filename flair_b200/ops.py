@@ -269,9 +269,10 @@ _GN_COUNTERS = {}
 
 
 def _gn_counter(device, B):
-    """Zeroed ticket counters of flair_gn_stats (self-cleaning; one buffer per device and stream, allocated on the
-    first eager call, i.e. before any CUDA-graph capture)."""
-    key = (device, _stream())
+    """Zeroed ticket counters of flair_gn_stats (self-cleaning).  One buffer per device, allocated on the first eager
+    call (before any CUDA-graph capture: every captured forward is preceded by an eager warm-up); all launches of a
+    process are stream-ordered (one stream per process), which is what sharing the counter requires."""
+    key = device
     c = _GN_COUNTERS.get(key)
     if c is None or c.numel() < B:
         c = torch.zeros(max(B, 64), dtype=torch.int32, device=device)

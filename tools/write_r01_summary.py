@@ -15,6 +15,7 @@ for k, v in tot.most_common(16):
 b = json.load(open('profiles/r01_bench_n1.json'))
 b2 = json.load(open('profiles/r01_bench_n2.json'))
 ref = json.load(open('profiles/r01_bench_reference_arm.json'))
+hbm = open('profiles/r01_hbm_probe.txt').read().strip()
 md = f"""# Round 1 — measured summary (B200, SM 1965 MHz under load, no throttle reasons)
 
 All numbers below were produced by commands in this repo on `gpurun` boxes; raw files are next to this one.
@@ -28,14 +29,27 @@ All numbers below were produced by commands in this repo on `gpurun` boxes; raw 
 | end of round 1, N=2, weak scaling, 1 step (`r01_bench_n2.json`) | {b2['value']:.3f} | {b2['e2e']['value']:.3f} | {b2['ms_per_step']/1e3:.2f} | — |
 | `--impl reference` (oracle port on the box's 16 host cores, bounded sample) | {ref['value']:.6f} | — | — | 0 |
 
-* UNet forward (T=10, 256x256, graph replay): 88.7 ms -> **69.6 ms** = {b['config']['unet_fwd_tflops_algorithmic']:.0f} TFLOP/s algorithmic
+* UNet forward (T=10, 256x256, graph replay): 88.7 ms -> **66.0 ms** (19.8 ms without the BasicVSR++ modules) = {b['config']['unet_fwd_tflops_algorithmic']:.0f} TFLOP/s algorithmic
   ({100*b['config']['unet_fwd_frac_of_peak']:.1f} % of the measured 1394.8 TFLOP/s sustained peak).
 * roofline (dominant kernel `conv_igemm_kernel`): {b['roofline']['launches']} launches per forward, {b['roofline']['alg_gflop_per_forward']/1e3:.1f} TFLOP
   algorithmic, average launch {b['roofline']['avg_launch_us']:.1f} us -> **{b['roofline']['achieved']:.0f} TFLOP/s = {100*b['roofline']['frac']:.1f} % of peak**
   (all conv launches of a forward replayed back to back from a CUDA graph, CUDA events).
 * e2e == value to 4 digits: the per-step H2D (0.79 MB) and D2H (12.6 MB) copies are ~0.5 ms against 12.8 s.
 
+## Memory-bound kernels against the measured HBM copy peak (6559 GB/s), `tests/gpu_probes/hbm_probe.py`
+
+Device time from CUDA-graph replays, 4 rotated buffer sets (> L2), algorithmic bytes as in DESIGN.md §3:
+
+```
+{hbm}
+```
+
+GroupNorm at the start of the session: stats 1.75 TB/s, apply 1.65 / 1.1 / 0.64 TB/s (ncu `r01_gn`: DRAM 23 % / 19 %
+busy, occupancy 25 % / 47 %, nothing else above 40 %: latency-bound, plus a 300-load statistics reduction in the prologue of
+every apply CTA).  The sampler tail at the start: 39x39 filter 402 us, fused update with in-register Up 301 us per 64 frames.
+
 ## ncu launch list of the bench command
+(taken before the GroupNorm / degradation-kernel work of the last commits; conv and deform_conv are unchanged since)
 
 `ncu --metrics gpu__time_duration.sum --clock-control none -c 6200 --csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline`
 (whole list per kernel: `r01_bench_launches.md`). Table: the first video-mode forward of the run (launches 1249..5451;
