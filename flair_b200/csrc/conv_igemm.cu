@@ -46,6 +46,7 @@ struct ConvKArgs {
   int tmem_cols;
   int Cout, Cout_pad;
   int kblocks, ntaps, stride;
+  int trace;   // debug timeline on/off
   int k_last;  // UMMA K=16 steps that hold real channels in the LAST k-block (Cin = 196: 1 of 4)
   int stages;
   // mode 0: one (tap, k-block) per pipeline stage, A tile = 128 output pixels.
@@ -79,6 +80,12 @@ struct ConvKArgs {
   int out2_gs;             // entry p = (pixel p, pixel p+1), the source layout of flair_deform_conv
   long long out2_gstride;  // elements between group planes
 };
+
+// Debug timeline (FLAIR_CONV_TRACE=1): CTA 0 records clock64() at a few points; read with flair_debug_conv_trace.
+__device__ long long g_conv_trace[16];
+__device__ __forceinline__ void trace_mark(int on, int slot) {
+  if (on && blockIdx.x == 0) g_conv_trace[slot] = clock64();
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -271,6 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvKArgs a) {
   pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
+  if (threadIdx.x == 0) trace_mark(a.trace, 0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(16) float s_bias[2][256];
   // carve: [resident weights (mode 2)] [stages][A][B] then barriers
@@ -312,6 +320,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_mark(a.trace, 1);
   pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   // tile walk of this CTA: (m_idx, n_idx) = f(local iteration)
@@ -344,9 +353,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       int stage = 0;
       uint32_t phase = 0;
+      trace_mark(a.trace, 2);
       for (int i = 0; i < my_tiles; ++i) {
         int m_idx, n_idx;
         tile_at(i, m_idx, n_idx);
+        if (i == 1) trace_mark(a.trace, 3);
         const int tw = m_idx % a.tiles_w; m_idx /= a.tiles_w;
         const int th = m_idx % a.tiles_h; m_idx /= a.tiles_h;
         const int tt = m_idx % a.tiles_t;
@@ -409,6 +420,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(w_bar, 0);
       tc_fence_after();
     }
+    if (lane == 0) trace_mark(a.trace, 4);
     const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // SBO, version, swizzle mode
     const uint32_t desc_lo_flags = static_cast<uint32_t>(umma_desc_sw128(0));  // LBO field
     const uint32_t stage0_lo = (smem_u32(smem) & 0x3FFFF) >> 4;
@@ -423,6 +435,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * a.acc_cols);
+      if (lane == 0 && local < 4) trace_mark(a.trace, 5 + local);  // MMA of tile `local` may start (TMEM buffer free)
       uint32_t accum = 0;  // first MMA of the tile overwrites the accumulator
       if (a.mode == 0) {
         int kb = 0;
@@ -544,6 +557,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (etid == 0 && local < 4) trace_mark(a.trace, 9 + local);  // accumulator of tile `local` complete
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * a.acc_cols) +
                               (static_cast<uint32_t>(quarter * 32) << 16);
       switch (kind * 4 + a.act) {
@@ -562,8 +576,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   }
 
+  if (threadIdx.x == 64) trace_mark(a.trace, 13);  // first epilogue thread done with all its tiles
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_mark(a.trace, 14);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(a.tmem_cols));
@@ -592,6 +608,11 @@ int pow2_ceil(int v) {
 }
 
 }  // namespace
+
+extern "C" int flair_debug_conv_trace(long long* host_out16) {
+  FLAIR_CHECK_CUDA(cudaMemcpyFromSymbol(host_out16, g_conv_trace, sizeof(long long) * 16));
+  return 0;
+}
 
 extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -667,6 +688,11 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   a.Cout = p->Cout; a.Cout_pad = Cout_pad;
   a.kblocks = Cin_pad / kBlockK;
   a.k_last = ceil_div(p->Cin - (a.kblocks - 1) * kBlockK, kUmmaK);
+  {
+    static int trace = -1;
+    if (trace < 0) { const char* e = getenv("FLAIR_CONV_TRACE"); trace = (e && e[0] == '1') ? 1 : 0; }
+    a.trace = trace;
+  }
   a.stride = s;
   int nt = 0;
   for (int dt = -(p->kt / 2); dt <= p->kt / 2; ++dt)

@@ -85,8 +85,18 @@ could be two mbarrier phases ahead of the MMA and a parity wait cannot see that 
 | 128->128 3x3, ONE 128x128 frame (380 per forward) | 17.4 us | 14 % | 53.5 MB (4.6 MB of input) | 128 CTAs x 1 tile, each pulls all 295 KB of weights: weight traffic is 2.4x the activation traffic |
 | 64->64 3x3, 10 frames batched (17 per forward) | 94.5 -> 77.0 us (`elect.sync` issue) | 46 % before | 119 MB DRAM | 627 TFLOP/s; N = 64 tiles are capped at ~67 % by the A-operand shared-memory reads |
 
-The serial propagation (200 steps x 9 dependent launches per forward) therefore runs at the L2->SM fabric rate.
-Next step: cluster launch + TMA multicast of the weight slabs.
+Intra-kernel timeline of CTA 0 (`FLAIR_CONV_TRACE=1`, `tests/gpu_probes/conv_trace.py`, `r01_conv_trace.txt`):
+
+| launch (kernel time) | CTA lifetime | prologue -> first MMA | per tile | last accumulator -> exit |
+|---|---:|---:|---:|---:|
+| 64->64, one 256x256 frame (19.4 us) | 9.96 us | 2.30 us (1.5 us of it issuing the 9 resident-weight TMA loads) | 1.65 us (36 MMAs = 0.9 us of tensor time: waits for the 3 halo slabs, 60 KB per tile) | 1.0 us |
+| 128->128, one 128x128 frame (17.4 us) | 7.05 us | 0.96 us | 4.05 us (72 MMAs = 2.3 us: waits for 410 KB, mostly weights) | 2.0 us (epilogue of the only tile, not overlapped) |
+
+Roughly half of the duration of a per-frame launch is outside the lifetime of a CTA (launch ramp, slower CTAs, drain), and
+inside it the MMAs wait for operand bytes.  With ~1800 such launches per forward this fixed cost is ~15 ms.
+Next steps: (1) per-frame kernels at <= 110 KB shared memory / <= 96 registers so that two launches
+co-reside, programmatic dependent launch with the trigger at the top and the wait after the prologue + weight
+prefetch; (2) cluster launch + TMA multicast of the weight slabs; (3) one halo slab per k-block for all nine taps.
 """
 open('profiles/r01_summary.md', 'w').write(md)
 print(md[:1500])
