@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
+    *(["-DFLAIR_CONV_TRACE_BUILD"] if os.environ.get("FLAIR_BUILD_TRACE") == "1" else []),
     "-Xptxas", "-v",
 ]
 

@@ -81,10 +81,14 @@ struct ConvKArgs {
   long long out2_gstride;  // elements between group planes
 };
 
-// Debug timeline (FLAIR_CONV_TRACE=1): CTA 0 records clock64() at a few points; read with flair_debug_conv_trace.
+// Debug timeline: in a library built with -DFLAIR_CONV_TRACE_BUILD (FLAIR_BUILD_TRACE=1 python -m flair_b200.build)
+// and run with FLAIR_CONV_TRACE=1, CTA 0 records clock64() at a few points; read with flair_debug_conv_trace.
+// Compiled out otherwise (the marks sit in the TMA / MMA issue loops).
 __device__ long long g_conv_trace[16];
 __device__ __forceinline__ void trace_mark(int on, int slot) {
+#ifdef FLAIR_CONV_TRACE_BUILD
   if (on && blockIdx.x == 0) g_conv_trace[slot] = clock64();
+#endif
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {

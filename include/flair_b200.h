@@ -106,8 +106,9 @@ typedef struct flair_conv_params {
 } flair_conv_params;
 
 int flair_conv_igemm(const flair_conv_params* p, void* stream);
-/* debug: with FLAIR_CONV_TRACE=1, CTA 0 of every conv launch records clock64() at 15 points (see conv_igemm.cu);
- * copies the 16 values of the most recent launch to the host (synchronises). */
+/* debug: in a library built with -DFLAIR_CONV_TRACE_BUILD and run with FLAIR_CONV_TRACE=1, CTA 0 of every conv
+ * launch records clock64() at 15 points (see conv_igemm.cu); copies the 16 values of the most recent launch to
+ * the host (synchronises).  All zeros in a normal build. */
 int flair_debug_conv_trace(long long* host_out16);
 
 /* ------------------------------------------------------------------------

@@ -1,4 +1,6 @@
-"""GPU probe: intra-kernel timeline of CTA 0 of a conv launch (FLAIR_CONV_TRACE=1)."""
+"""GPU probe: intra-kernel timeline of CTA 0 of a conv launch.  Needs a library built with the trace marks:
+    touch flair_b200/csrc/conv_igemm.cu; FLAIR_BUILD_TRACE=1 python -m flair_b200.build
+(rebuild without the variable afterwards: the marks sit in the issue loops)."""
 import ctypes, os, sys
 os.environ["FLAIR_CONV_TRACE"] = "1"
 import torch
