@@ -347,7 +347,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // elect.sync instead of `lane == 0`: the compiler then keeps coordinates / addresses in uniform registers and
+    // emits a bare UTMALDG; under `lane == 0` every TMA issue was a waterfall loop (ELECT + 7 R2UR.BROADCAST +
+    // branch), ~300 cycles per issue — with 4 loads per stage that, not bandwidth, bounded the streamed-weight mode.
+    if (elect_one()) {
       if (resident) {  // this CTA's weights: every (tap, k-block) slab of its N tile, once
         mbar_expect_tx(w_bar, a.w_bytes);
         for (int tap = 0; tap < a.ntaps; ++tap)

@@ -224,7 +224,7 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA: offset rows per tap, weight slab per k-block =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0, os = 0;
       uint32_t phase = 0, ophase = 0;
       for (int i = 0; i < my_tiles; ++i) {
