@@ -77,26 +77,36 @@ slot was released right after the `ld.shared` were issued (nothing made the arri
 sampled with the offsets of a later tap); (2) with fewer pipeline stages than k-blocks per tap a producer warp
 could be two mbarrier phases ahead of the MMA and a parity wait cannot see that (non-deterministic results at C=128).
 
-## Why the per-frame BasicVSR++ convs are slow (`r01_conv64_t1_ncu_details.txt`, `r01_conv128_t1_ncu_details.txt`)
+## Per-frame BasicVSR++ convs: device time per launch inside a CUDA graph (`tests/gpu_probes/conv_graph.py`)
 
-| launch | time | tensor pipe busy | L2->SM bytes | note |
-|---|---:|---:|---:|---|
-| 64->64 3x3, ONE 256x256 frame (380 per forward) | 19.4 us | 20 % | 42 MB (8.5 MB of input) | 4 tiles per CTA; A halo slabs re-read 3x + 73 KB resident weights per CTA |
-| 128->128 3x3, ONE 128x128 frame (380 per forward) | 17.4 us | 14 % | 53.5 MB (4.6 MB of input) | 128 CTAs x 1 tile, each pulls all 295 KB of weights: weight traffic is 2.4x the activation traffic |
-| 64->64 3x3, 10 frames batched (17 per forward) | 94.5 -> 77.0 us (`elect.sync` issue) | 46 % before | 119 MB DRAM | 627 TFLOP/s; N = 64 tiles are capped at ~67 % by the A-operand shared-memory reads |
+A chain of identical launches replayed from a graph (no host cost; operands L2-warm as in the model, where the input
+was written by the previous kernel).  ncu's isolated `gpu__time_duration` of the same launches is 1.6-1.8x larger
+(cold caches, serialised), and a Python loop over `ops.conv` is host-bound at ~16 us per call — neither is the in-situ cost.
 
-Intra-kernel timeline of CTA 0 (`FLAIR_CONV_TRACE=1`, `tests/gpu_probes/conv_trace.py`, `r01_conv_trace.txt`):
+| launch (per forward) | us per launch | TFLOP/s | % of 1394.8 |
+|---|---:|---:|---:|
+| 64->64 3x3, one 256x256 frame (380) | 12.3 | 393 | 28 % |
+| 128->128 3x3, one 128x128 frame (380) | 9.7 | 499 | 36 % |
+| 192->64 3x3, one 256x256 frame (50) | 22.8 | 636 | 46 % |
+| 64->432 3x3, one 256x256 frame (90) | 38.2 | 853 | 61 % |
+| 384->128 3x3, one 128x128 frame (50) | 16.8 | 862 | 62 % |
+| 128->432 3x3, one 128x128 frame (90) | 20.1 | 812 | 58 % |
+| 64->64 3x3, 10 frames batched (17) | 68.3 (94.5 at the start of the session) | 707 | 51 % |
 
-| launch (kernel time) | CTA lifetime | prologue -> first MMA | per tile | last accumulator -> exit |
-|---|---:|---:|---:|---:|
-| 64->64, one 256x256 frame (19.4 us) | 9.96 us | 2.30 us (1.5 us of it issuing the 9 resident-weight TMA loads) | 1.65 us (36 MMAs = 0.9 us of tensor time: waits for the 3 halo slabs, 60 KB per tile) | 1.0 us |
-| 128->128, one 128x128 frame (17.4 us) | 7.05 us | 0.96 us | 4.05 us (72 MMAs = 2.3 us: waits for 410 KB, mostly weights) | 2.0 us (epilogue of the only tile, not overlapped) |
+CTA-0 timeline of the two smallest (`r01_conv_trace.txt`, trace build): 64->64: lifetime 9.96 us = 2.3 us to the first
+MMA (1.5 us of it issuing the 9 resident-weight TMA loads, before `elect.sync`) + 4 tiles x 1.65 us (36 MMAs = 0.9 us of
+tensor time; the rest waits for the three 20 KB halo slabs of the tile: the input is re-read 3x) + 1.0 us epilogue tail;
+128->128: 7.05 us = 0.96 + 4.05 (72 MMAs = 2.3 us; 410 KB per tile, mostly weights) + 2.0 us epilogue of its only tile.
+N = 64 tiles are additionally capped at ~67 % by the A-operand shared-memory reads.  Two issue-path fixes came out of
+this: the MMA and TMA lanes are now chosen with `elect.sync` (the compiler had wrapped every `tcgen05.mma` / `UTMALDG`
+issued under `lane == 0` in a 10-17 instruction waterfall loop).
 
-Roughly half of the duration of a per-frame launch is outside the lifetime of a CTA (launch ramp, slower CTAs, drain), and
-inside it the MMAs wait for operand bytes.  With ~1800 such launches per forward this fixed cost is ~15 ms.
-Next steps (DESIGN.md §8): (1) per-frame kernels at <= 110 KB shared memory / <= 96 registers so that two launches
-co-reside, programmatic dependent launch with the trigger at the top and the wait after the prologue + weight
-prefetch; (2) cluster launch + TMA multicast of the weight slabs; (3) one halo slab per k-block for all nine taps.
+The serial propagation is 200 steps x 9 dependent launches per forward: ~230 us per step at C = 64 (deform 85, 64->432 38,
+196->64 23, 4 x 12.3, backbone first conv 20, warps 10) and ~150 us at C = 128.
+Next steps (DESIGN.md §8): per-frame kernels small enough for two launches to co-reside + programmatic dependent launch
+with the weight prefetch before the wait; cluster launch + TMA multicast of the weight slabs; one halo slab per k-block
+for all nine taps; L1 hit rate of the deformable gather (26 % with the pair planes, `r01_deform_v4_ncu_details.txt`:
+l1tex 88 % busy, L2 36 %).
 """
 open('profiles/r01_summary.md', 'w').write(md)
 print(md[:1500])
