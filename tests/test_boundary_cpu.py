@@ -140,3 +140,23 @@ def test_wrapped_model_dispatches_on_sr3(golden):
     assert isinstance(w, _WrappedModel)
     w(torch.zeros(2, 3, 4, 4), torch.tensor([99, 0]))
     assert torch.allclose(seen["level"], torch.tensor(d.sqrt_alphas_cumprod_prev[[100, 1]], dtype=torch.float32))
+
+
+def test_deform_offset_permutation_and_pair_planes():
+    """Host-side layout helpers of the fused deformable alignment: the tap-major permutation of the offset-net output
+    channels (include/flair_b200.h, flair_deform_conv) and the pair-plane layout of its sources."""
+    from flair_b200 import ops
+    perm = ops.deform_offset_perm(16)
+    assert sorted(perm.tolist()) == list(range(432))
+    # new channel tap*48 + quad*12 + kind*4 + gi  <-  reference dy/dx at (g*9+tap)*2+{0,1}, mask at 288 + g*9 + tap
+    for tap, quad, kind, gi in [(0, 0, 0, 0), (4, 2, 1, 3), (8, 3, 2, 1), (5, 1, 0, 2)]:
+        g = quad * 4 + gi
+        ref = (g * 9 + tap) * 2 + kind if kind < 2 else 288 + g * 9 + tap
+        assert int(perm[tap * 48 + quad * 12 + kind * 4 + gi]) == ref
+    x = torch.arange(2 * 3 * 4 * 16, dtype=torch.float32).reshape(2, 3, 4, 16)   # [N,H,W,C], C/8 = 2 channels per group
+    P = ops.pair_planes(x)
+    assert P.shape == (8, 24, 2, 2)
+    flat = x.reshape(24, 8, 2)
+    assert torch.equal(P[:, :, 0], flat.permute(1, 0, 2))                    # slot 0: pixel p
+    assert torch.equal(P[:, :-1, 1], flat.permute(1, 0, 2)[:, 1:])           # slot 1: pixel p+1 (row-major, across rows/images)
+    assert float(P[:, -1, 1].abs().max()) == 0.0                             # last entry: zeros

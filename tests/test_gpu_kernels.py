@@ -126,6 +126,38 @@ def test_flow_warp(dev):
     assert _rel(y, K.flow_warp_cl(x, flow)) < 1e-3
 
 
+def test_flow_warp2_equals_two_warps(dev):
+    """The fused first-/second-order warp launch writes the same bits as two flow_warp launches, into channel slices."""
+    from flair_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    C, H, W = 64, 40, 24
+    xa, xb = torch.randn(1, H, W, C, generator=g).half().to(dev), torch.randn(1, H, W, C, generator=g).half().to(dev)
+    f1, f2 = (torch.randn(1, 2, H, W, generator=g) * 3).to(dev), (torch.randn(1, 2, H, W, generator=g) * 7).to(dev)
+    cond = torch.zeros(1, H, W, 3 * C + 8, dtype=torch.float16, device=dev)
+    ops.flow_warp2(xa, f1, cond[..., :C], xb, f2, cond[..., 2 * C:3 * C])
+    assert torch.equal(cond[..., :C], ops.flow_warp(xa, f1))
+    assert torch.equal(cond[..., 2 * C:3 * C], ops.flow_warp(xb, f2))
+    assert float(cond[..., C:2 * C].abs().max()) == 0.0 and float(cond[..., 3 * C:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,T,H,C,groups", [(1, 10, 64, 64, 32), (2, 3, 16, 192, 32), (1, 4, 8, 512, 32), (1, 2, 32, 128, 16)])
+def test_group_norm_statistics(dev, B, T, H, C, groups):
+    """flair_gn_stats: (mean, rstd) finalised by the last CTA of the launch == torch statistics; repeated launches
+    agree bit for bit (the ticket counter is self-cleaning, the reduction order is fixed)."""
+    from flair_b200 import ops
+    g = torch.Generator().manual_seed(C + T)
+    x = (torch.randn(B, T, H, H, C, generator=g) * 2.3 - 0.7).half()
+    xd = x.to(dev)
+    fin, n = ops.gn_stats(xd, groups)
+    assert n == 0 and fin.shape == (B, groups, 2)
+    xf = x.float().reshape(B, T * H * H, groups, C // groups).permute(0, 2, 1, 3).reshape(B, groups, -1).double()
+    mean, var = xf.mean(-1), xf.var(-1, unbiased=False)
+    assert _rel(fin[..., 0], mean) < 1e-5
+    assert _rel(fin[..., 1], 1.0 / torch.sqrt(var + 1e-5)) < 1e-5
+    for _ in range(3):
+        assert torch.equal(ops.gn_stats(xd, groups)[0], fin)
+
+
 DEFORM_CASES = [(64, 16, 24, 1, torch.float16), (64, 40, 40, 2, torch.float16), (128, 24, 16, 1, torch.float16),
                 (64, 32, 32, 1, torch.bfloat16), (128, 32, 32, 1, torch.float16), (64, 160, 160, 1, torch.float16)]
 
