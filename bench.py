@@ -283,7 +283,12 @@ def conv_roofline(model, ops, dev, pk):
         kw2["out"] = y if not kw.get("nchw_out") else None
         if kw2["out"] is None:
             kw2.pop("out")
-        rec.append(((x, wpk, cout, ksize), kw2, 2.0 * B * F_ * (H // s) * (W // s) * cin * cout * ksize[0] * ksize[1] * ksize[2]))
+        taps = ksize[0] * ksize[1] * ksize[2]
+        nbytes = x.numel() * x.element_size() + y.numel() * y.element_size() + taps * cout * cin * 2
+        for r in ("residual", "residual2"):
+            if kw.get(r) is not None:
+                nbytes += y.numel() * kw[r].element_size()
+        rec.append(((x, wpk, cout, ksize), kw2, 2.0 * B * F_ * (H // s) * (W // s) * cin * cout * taps, nbytes))
         return y
 
     clip = (synth.synthetic_clip(T, SIZE) * 2 - 1).to(dev)
@@ -304,7 +309,7 @@ def conv_roofline(model, ops, dev, pk):
         model.use_cuda_graph = graph_flag
 
     def replay_all():
-        for a, kw, _ in rec:
+        for a, kw, _, _ in rec:
             real(*a, **kw)
 
     side = torch.cuda.Stream()
@@ -325,10 +330,22 @@ def conv_roofline(model, ops, dev, pk):
     e1.record()
     torch.cuda.synchronize()
     secs = e0.elapsed_time(e1) / 1e3 / reps
-    flops = sum(f for _, _, f in rec)
+    flops = sum(f for _, _, f, _ in rec)
+    alg_bytes = sum(nb for _, _, _, nb in rec)
     achieved = flops / secs / 1e12
+    # DRAM bytes per launch of the same 1622 launches from an ncu capture (profiles/r01_conv_traffic.json; ncu cannot
+    # run inside the bench).  Next to it: the algorithmic bytes (operands + result + residuals, each once).
+    traffic = traffic_note = None
+    tj = ROOT / "profiles" / "r01_conv_traffic.json"
+    if tj.exists():
+        t = json.loads(tj.read_text())
+        traffic = t["dram_bytes_per_launch"]
+        traffic_note = {"source": "profiles/r01_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                                  "average over the conv launches of one forward, cold-cache)",
+                        "l2_to_sm_bytes_per_launch": t["l2_to_sm_bytes_per_launch"]}
     return {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05/TMA implicit GEMM)", "achieved": achieved,
-            "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+            "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
+            "traffic_note": traffic_note, "alg_bytes_per_launch": alg_bytes / len(rec),
             "peak_source": pk["src"] + " (bf16_tflops_sustained; fp16 and bf16 share the kind::f16 pipe)",
             "launches": len(rec), "avg_launch_us": secs / len(rec) * 1e6, "alg_gflop_per_forward": flops / 1e9,
             "how": "all conv launches of one video-mode forward (T=10, 256x256) replayed back to back from a CUDA "

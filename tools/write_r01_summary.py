@@ -34,7 +34,11 @@ All numbers below were produced by commands in this repo on `gpurun` boxes; raw 
 * roofline (dominant kernel `conv_igemm_kernel`): {b['roofline']['launches']} launches per forward, {b['roofline']['alg_gflop_per_forward']/1e3:.1f} TFLOP
   algorithmic, average launch {b['roofline']['avg_launch_us']:.1f} us -> **{b['roofline']['achieved']:.0f} TFLOP/s = {100*b['roofline']['frac']:.1f} % of peak**
   (all conv launches of a forward replayed back to back from a CUDA graph, CUDA events).
-* e2e == value to 4 digits: the per-step H2D (0.79 MB) and D2H (12.6 MB) copies are ~0.5 ms against 12.8 s.
+* traffic of those launches (`r01_conv_traffic.json`, ncu over the 1622 conv launches of one forward): DRAM
+  {b['roofline']['traffic']/1e6:.1f} MB per launch against {b['roofline']['alg_bytes_per_launch']/1e6:.1f} MB algorithmic (operands + result + residuals once: the L2 keeps what
+  the previous kernel wrote), but **{b['roofline']['traffic_note']['l2_to_sm_bytes_per_launch']/1e6:.0f} MB per launch L2->SM = 3.3x the algorithmic bytes**: halo slabs re-read per dw
+  shift and the whole filter pulled by every CTA — the re-reads to remove next.
+* e2e == value to 4 digits: the per-step H2D (0.79 MB) and D2H (12.6 MB) copies are ~0.5 ms against {b['ms_per_step']/1e3:.1f} s.
 
 ## Memory-bound kernels against the measured HBM copy peak (6559 GB/s), `tests/gpu_probes/hbm_probe.py`
 
