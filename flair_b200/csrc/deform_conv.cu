@@ -4,24 +4,32 @@
 // Replaces SecondOrderDeformableAlignment.forward after the offset net (reference
 // guided_diffusion/unet_new.py:874-898; unet.py:469-492): offset = mrm * tanh(cat(o1, o2)) + flipped
 // flows, mask = sigmoid(.), torchvision.ops.deform_conv2d(cat(feat_prop, feat_n2), offset, weight,
-// bias, padding 1, mask).  The previous two-kernel version (flair_deform_im2col + 1x1 GEMM) wrote
-// and re-read 18C x 2 B per pixel (151 MB per 256x256 frame at C = 64) and was bound by L1
-// wavefronts of scattered 16-byte gathers (153 us per launch, 28 % of the whole UNet forward).
+// bias, padding 1, mask).  The two-kernel version (flair_deform_im2col + 1x1 GEMM, still the generic path) wrote
+// and re-read 18C x 2 B per pixel (151 MB per 256x256 frame at C = 64): 217 + 34 us per frame; this kernel: 107 us
+// (89 us inside the model), 59-63 us vs 93 + 21 us at C = 128 on a 128x128 frame.
 //
-// Roles (14 warps): warp 0 = TMA (weight slabs + offset rows), warp 1 = tcgen05.mma issuer,
-// warps 2..5 = epilogue (TMEM -> +bias -> 16-bit NHWC), warps 6..13 = gather producers.
-// M tile = 128 consecutive pixels, N = C, K = 9 taps x 2C walked in 64-channel k-blocks
-// (k = tap * 2C + channel of cat(xa, xb), the layout flair_deform_im2col used, so the packed
-// weight is unchanged).  A producer warp owns 32 pixel rows x the 8 deform groups of one source: per tap
-// it reads its (dy, dx, mask) triples from the TMA-staged offset rows, gathers 4 corners x (C/64) 16-byte vectors
-// per group, blends in fp32 and writes the 16-byte chunks straight into the 128B-swizzled K-major
-// operand tile the MMA consumes (generic-proxy stores + fence.proxy.async + mbarrier arrive).
+// Roles (22 warps, one CTA per SM, persistent over 16 x 8-pixel tiles): warp 0 = TMA (one weight slab per
+// k-block; the 48 offset-net channels of the current tap for the whole tile, one 4-D box), warp 1 = tcgen05.mma
+// issuer (elect.sync), warps 2..5 = epilogue (TMEM -> +bias -> 16-bit NHWC, output may be a channel slice),
+// warps 6..21 = gather producers.  M tile = 128 pixels, N = C, K = 9 taps x 2C walked in 64-channel k-blocks
+// (k = tap * 2C + channel of cat(xa, xb), the layout flair_deform_im2col used, so the packed weight is unchanged).
+// A producer warp owns 32 tile rows (lane = pixel) x 4 deform groups: per tap it reads its (dy, dx, mask) triples
+// from the staged offset rows, computes the sample positions, loads the two x-corner pairs (one row each) of every
+// group with 32-byte loads, blends (fp16: half2 FMAs like the reference's fp16 torchvision kernel; bf16: fp32) and
+// writes the 16-byte chunks straight into the 128B-swizzled K-major operand tile the MMA consumes
+// (st.shared + fence.proxy.async + mbarrier arrive by every lane).
 //
-// Source layout.  With NHWC sources the 32 lanes of a gather (32 neighbouring pixels, one deform
-// group) touch 32 different 128-byte lines.  The caller may instead pass group-major planes
-// [group][pixel][C/8 channels] (conv epilogue `out2`, see flair_conv_params): neighbouring pixels of
-// one group are then contiguous and a warp-wide gather touches ~4-8 lines.  Both are described by
-// (group stride, pixel stride) in elements.
+// Source layout: pair planes [8 groups][pixel][2][C/8] written by the conv epilogue (`out2` of flair_conv_params):
+// entry p = (pixel p, pixel p+1) of the row-major map, so both x-corners of a bilinear sample are one aligned
+// 32-byte (C = 64) or two 32-byte (C = 128) loads: 2 L1 tag look-ups per sample instead of 4.  The kernel is bound
+// by those look-ups (ncu: l1tex 88 % busy); shared memory is kept to 128-156 KB so that ~100 KB of L1 remain for the
+// ~36x re-read of every source pixel.
+//
+// Ring invariants (both were violated once and produced rare wrong pixels, see profiles/r01_summary.md):
+//  * the offset slot of a tap is released at the END of the tap, after its values were consumed — an arrive issued
+//    right after the ld.shared does not wait for the loads;
+//  * stages >= k-blocks per tap: the k-blocks of a tap are produced by different warps that throttle only on their
+//    own stage, and a parity wait cannot distinguish "two phases ahead".
 //
 // Offset-net output layout.  The caller permutes the output channels of the last offset conv at
 // weight-pack time so that the 48 values one tap needs are contiguous per pixel:
