@@ -177,9 +177,9 @@ def run_native(args):
     dev = torch.device("cuda", local)
     L.check(L.lib().flair_check_device(local))
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG >= VERSION (WARN included)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=dev)
     torch.set_grad_enabled(False)
 

@@ -31,6 +31,9 @@ All numbers below were produced by commands in this repo on `gpurun` boxes; raw 
 
 * UNet forward (T=10, 256x256, graph replay): 88.7 ms -> **66.0 ms** (19.8 ms without the BasicVSR++ modules) = {b['config']['unet_fwd_tflops_algorithmic']:.0f} TFLOP/s algorithmic
   ({100*b['config']['unet_fwd_frac_of_peak']:.1f} % of the measured 1394.8 TFLOP/s sustained peak).
+* one clip sharded over 2 GPUs with `flair_b200.parallel` (NCCL point-to-point scatter of the segments incl. the 3 overlap
+  frames, per-rank chained windows, NCCL gather + stitching; `tests/gpu_probes/sharded_probe.py` under torchrun on
+  2 x B200): bit-identical to the same segments restored locally.
 * SR3 (x8/x16 bicubic) UNet forward, video mode T=10, 256x256 (`tests/gpu_probes/sr3_perf_probe.py`): 27.6 ms = 358 TFLOP/s
   algorithmic (988.1 GF/frame with SPyNet cached).
 * roofline (dominant kernel `conv_igemm_kernel`): {b['roofline']['launches']} launches per forward, {b['roofline']['alg_gflop_per_forward']/1e3:.1f} TFLOP
