@@ -89,6 +89,53 @@ struct Warp2Args {
   uint16_t* out[2];
   int x_cstride[2];
 };
+// one bilinear sample of an 8-channel vector: corner loads are always issued (clamped address, weight 0 outside the
+// map — identical bits to skipping the corner), so two items per thread can have their 8 loads in flight together
+struct WarpItem {
+  uint4 v[4];
+  float w[4];
+};
+__device__ __forceinline__ void warp_item_load(WarpItem& it, const uint16_t* __restrict__ x, const float* __restrict__ flow,
+                                               long long n, long long off, long long hw, int H, int W, int x_cstride, int cv) {
+  const int h = static_cast<int>(off / W), w = static_cast<int>(off % W);
+  const float sx = w + __ldg(flow + (n * 2 + 0) * hw + off);
+  const float sy = h + __ldg(flow + (n * 2 + 1) * hw + off);
+  const float fx0 = floorf(sx), fy0 = floorf(sy);
+  const int x0 = static_cast<int>(fmaxf(fminf(fx0, static_cast<float>(W)), -2.f));
+  const int y0 = static_cast<int>(fmaxf(fminf(fy0, static_cast<float>(H)), -2.f));
+  const float ax = sx - fx0, ay = sy - fy0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int dy = c >> 1, dx = c & 1;
+    const int xx = x0 + dx, yy = y0 + dy;
+    const bool in = xx >= 0 && xx < W && yy >= 0 && yy < H;
+    it.w[c] = in ? (dx ? ax : 1.f - ax) * (dy ? ay : 1.f - ay) : 0.f;
+    const int xc = min(max(xx, 0), W - 1), yc = min(max(yy, 0), H - 1);
+    it.v[c] = __ldg(reinterpret_cast<const uint4*>(x + (n * hw + static_cast<long long>(yc) * W + xc) * x_cstride + cv * 8));
+  }
+}
+__device__ __forceinline__ void warp_item_store(const WarpItem& it, uint16_t* __restrict__ out, long long pix, int out_cstride,
+                                                int cv, int dtype) {
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t wd[4] = {it.v[c].x, it.v[c].y, it.v[c].z, it.v[c].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f;
+      if (dtype == FLAIR_F16) {
+        __half2 hh = *reinterpret_cast<const __half2*>(&wd[i]);
+        f = __half22float2(hh);
+      } else {
+        f = unpack_bf16x2(wd[i]);
+      }
+      acc[2 * i] = fmaf(it.w[c], f.x, acc[2 * i]);
+      acc[2 * i + 1] = fmaf(it.w[c], f.y, acc[2 * i + 1]);
+    }
+  }
+  st8(out + pix * out_cstride + cv * 8, dtype, acc);
+}
+
 __global__ void __launch_bounds__(256)
 flow_warp2_kernel(const __grid_constant__ Warp2Args a, int N, int H, int W, int C, int out_cstride, int dtype) {
   pdl_sync();
@@ -100,32 +147,20 @@ flow_warp2_kernel(const __grid_constant__ Warp2Args a, int N, int H, int W, int 
   const int vecs = C / 8;
   const long long hw = static_cast<long long>(H) * W;
   const long long items = static_cast<long long>(N) * hw * vecs;
-  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
-       it += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(it % vecs);
-    const long long pix = it / vecs;
-    const long long n = pix / hw;
-    const long long off = pix - n * hw;
-    const int h = static_cast<int>(off / W), w = static_cast<int>(off % W);
-    const float sx = w + __ldg(flow + (n * 2 + 0) * hw + off);
-    const float sy = h + __ldg(flow + (n * 2 + 1) * hw + off);
-    const float fx0 = floorf(sx), fy0 = floorf(sy);
-    const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
-    const float ax = sx - fx0, ay = sy - fy0;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int xx = x0 + dx, yy = y0 + dy;
-        if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
-        const float wgt = (dx ? ax : 1.f - ax) * (dy ? ay : 1.f - ay);
-        float v[8];
-        ld8(x + (n * hw + static_cast<long long>(yy) * W + xx) * x_cstride + cv * 8, dtype, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, v[j], acc[j]);
-      }
-    st8(out + pix * out_cstride + cv * 8, dtype, acc);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < items; i0 += 2 * stride) {
+    const long long i1 = i0 + stride;
+    const bool two = i1 < items;
+    WarpItem A, B;
+    const int cv0 = static_cast<int>(i0 % vecs);
+    const long long pix0 = i0 / vecs, n0 = pix0 / hw;
+    warp_item_load(A, x, flow, n0, pix0 - n0 * hw, hw, H, W, x_cstride, cv0);
+    const long long i1c = two ? i1 : i0;
+    const int cv1 = static_cast<int>(i1c % vecs);
+    const long long pix1 = i1c / vecs, n1 = pix1 / hw;
+    if (two) warp_item_load(B, x, flow, n1, pix1 - n1 * hw, hw, H, W, x_cstride, cv1);
+    warp_item_store(A, out, pix0, out_cstride, cv0, dtype);
+    if (two) warp_item_store(B, out, pix1, out_cstride, cv1, dtype);
   }
 }
 
