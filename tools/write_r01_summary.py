@@ -29,7 +29,7 @@ All numbers below were produced by commands in this repo on `gpurun` boxes; raw 
 | end of round 1, N=2, weak scaling, 1 step (`r01_bench_n2.json`) | {b2['value']:.3f} | {b2['e2e']['value']:.3f} | {b2['ms_per_step']/1e3:.2f} | — |
 | `--impl reference` (oracle port on the box's 16 host cores, bounded sample) | {ref['value']:.6f} | — | — | 0 |
 
-* UNet forward (T=10, 256x256, graph replay): 88.7 ms -> **66.0 ms** (19.8 ms without the BasicVSR++ modules) = {b['config']['unet_fwd_tflops_algorithmic']:.0f} TFLOP/s algorithmic
+* UNet forward (T=10, 256x256, graph replay): 88.7 ms -> **64.8 ms** (19.8 ms without the BasicVSR++ modules) = {b['config']['unet_fwd_tflops_algorithmic']:.0f} TFLOP/s algorithmic
   ({100*b['config']['unet_fwd_frac_of_peak']:.1f} % of the measured 1394.8 TFLOP/s sustained peak).
 * one clip sharded over 2 GPUs with `flair_b200.parallel` (NCCL point-to-point scatter of the segments incl. the 3 overlap
   frames, per-rank chained windows, NCCL gather + stitching; `tests/gpu_probes/sharded_probe.py` under torchrun on
