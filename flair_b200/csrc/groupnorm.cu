@@ -424,11 +424,24 @@ copy_channels_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, lon
                      int src_vstride, int dst_vstride, int dst_voff) {
   pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long items = P * vecs;
-  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
-       it += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long p = it / vecs;
-    const int v = static_cast<int>(it % vecs);
-    dst[p * dst_vstride + dst_voff + v] = __ldg(src + p * src_vstride + v);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  constexpr int kU = 4;  // independent 16-byte loads in flight per thread
+  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items; it += kU * stride) {
+    uint4 r[kU];
+    long long d[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = it + u * stride;
+      if (i < items) {
+        const long long p = i / vecs;
+        const int v = static_cast<int>(i - p * vecs);
+        r[u] = __ldg(src + p * src_vstride + v);
+        d[u] = p * dst_vstride + dst_voff + v;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (it + u * stride < items) dst[d[u]] = r[u];
   }
 }
 
