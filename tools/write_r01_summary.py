@@ -104,7 +104,8 @@ was written by the previous kernel).  ncu's isolated `gpu__time_duration` of the
 
 CTA-0 timeline of the two smallest (`r01_conv_trace.txt`, trace build): 64->64: lifetime 9.96 us = 2.3 us to the first
 MMA (1.5 us of it issuing the 9 resident-weight TMA loads, before `elect.sync`) + 4 tiles x 1.65 us (36 MMAs = 0.9 us of
-tensor time; the rest waits for the three 20 KB halo slabs of the tile: the input is re-read 3x) + 1.0 us epilogue tail;
+tensor time; the MMA warp waits for operand slabs in between — yet a single-slab variant that cut the A bytes by 40 %
+was no faster, so it is latency per stage, not bytes) + 1.0 us epilogue tail;
 128->128: 7.05 us = 0.96 + 4.05 (72 MMAs = 2.3 us; 410 KB per tile, mostly weights) + 2.0 us epilogue of its only tile.
 N = 64 tiles are additionally capped at ~67 % by the A-operand shared-memory reads.  Two issue-path fixes came out of
 this: the MMA and TMA lanes are now chosen with `elect.sync` (the compiler had wrapped every `tcgen05.mma` / `UTMALDG`
@@ -113,8 +114,7 @@ issued under `lane == 0` in a 10-17 instruction waterfall loop).
 The serial propagation is 200 steps x 9 dependent launches per forward: ~230 us per step at C = 64 (deform 85, 64->432 38,
 196->64 23, 4 x 12.3, backbone first conv 20, warps 10) and ~150 us at C = 128.
 Next steps (DESIGN.md §8): per-frame kernels small enough for two launches to co-reside + programmatic dependent launch
-with the weight prefetch before the wait; cluster launch + TMA multicast of the weight slabs; one halo slab per k-block
-for all nine taps; L1 hit rate of the deformable gather (26 % with the pair planes, `r01_deform_v4_ncu_details.txt`:
+with the weight prefetch before the wait; cluster launch + TMA multicast of the weight slabs; L1 hit rate of the deformable gather (26 % with the pair planes, `r01_deform_v4_ncu_details.txt`:
 l1tex 88 % busy, L2 36 %).
 """
 open('profiles/r01_summary.md', 'w').write(md)
