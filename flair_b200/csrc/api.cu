@@ -20,14 +20,16 @@ void flair_set_error(const char* fmt, ...) {
 }
 
 int flair_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static std::atomic<int> sms[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int v = sms[dev & 63].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    sms[dev & 63].store(v, std::memory_order_relaxed);
   }
-  return sms;
+  return v;
 }
 
 int flair_pdl_enabled() {

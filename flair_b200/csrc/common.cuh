@@ -48,7 +48,22 @@ void flair_set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
-int flair_num_sms();
+int flair_num_sms();  // SM count of the CURRENT device (cached per device)
+
+// One-time-per-DEVICE guard for cudaFuncSetAttribute (the attribute is per device; one process may drive several GPUs
+// through this C ABI).  `first()` returns true exactly once per device, thread-safely.
+#ifdef __cplusplus
+#include <atomic>
+struct FlairPerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (mask.fetch_or(bit) & bit) == 0;
+  }
+};
+#endif
 
 // Driver entry point for cuTensorMapEncodeTiled, fetched through the runtime so
 // the library has no link-time dependency on libcuda.

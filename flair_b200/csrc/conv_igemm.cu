@@ -62,6 +62,9 @@ struct ConvKArgs {
   int rowbias_stride;
   const float* rowscale;
   int rowscale_stride;
+  const void* preadd;  // added to the accumulator BEFORE the activation (precomputed partial convolution)
+  int preadd_dtype;
+  long long preadd_cstride;
   const void* residual;
   int residual_dtype;
   long long residual_cstride;
@@ -196,6 +199,8 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_
           if (n + j < a.Cout) v[j] += __ldg(rb + j);
       }
     }
+    if (a.preadd != nullptr && pos.valid)
+      add_residual(v, a.preadd, a.preadd_dtype, pos.pix * a.preadd_cstride + n, full16, a.Cout - n);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float y = v[j];
@@ -281,7 +286,10 @@ __device__ __forceinline__ void epilogue_cols(const ConvKArgs& a, uint32_t t_add
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvKArgs a) {
-  pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
+  // PDL: let the next launch's CTAs be scheduled as soon as SMs free up.  Nothing before pdl_wait() below touches
+  // memory written by an earlier kernel: barrier init, TMEM allocation, descriptor prefetch and the loads of this
+  // CTA's resident weights (constant since model load) all overlap the previous kernel's tail.
+  pdl_trigger();
   if (threadIdx.x == 0) trace_mark(a.trace, 0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(16) float s_bias[2][256];
@@ -296,8 +304,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* empty_bar = bars + a.stages;
   uint64_t* tfull_bar = bars + 2 * a.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* w_bar = tempty_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* w_bar = tempty_bar + 2;  // [ntd * 3]: resident weights arrive per (dt, dw) group, in the order the MMAs use them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 9);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -313,7 +321,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
-    mbar_init(w_bar, 1);
+    for (int g = 0; g < 9; ++g) mbar_init(&w_bar[g], 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -325,7 +333,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) trace_mark(a.trace, 1);
-  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+  // (pdl_wait() is executed per role below: the MMA warp first issues the weight loads)
 
   // tile walk of this CTA: (m_idx, n_idx) = f(local iteration)
   //   modes 0/1: linear tile id = blockIdx.x + i*gridDim.x, n fastest (neighbouring CTAs share A in L2)
@@ -350,14 +358,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // elect.sync instead of `lane == 0`: the compiler then keeps coordinates / addresses in uniform registers and
     // emits a bare UTMALDG; under `lane == 0` every TMA issue was a waterfall loop (ELECT + 7 R2UR.BROADCAST +
     // branch), ~300 cycles per issue — with 4 loads per stage that, not bandwidth, bounded the streamed-weight mode.
+    pdl_wait();  // activations are the previous kernel's output
     if (elect_one()) {
-      if (resident) {  // this CTA's weights: every (tap, k-block) slab of its N tile, once
-        mbar_expect_tx(w_bar, a.w_bytes);
-        for (int tap = 0; tap < a.ntaps; ++tap)
-          for (int kb = 0; kb < a.kblocks; ++kb)
-            tma_load_2d(smem_w + static_cast<size_t>(tap * a.kblocks + kb) * b_bytes, &tmB, w_bar, kb * kBlockK,
-                        tap * a.Cout_pad + my_n * a.n_tile);
-      }
       int stage = 0;
       uint32_t phase = 0;
       trace_mark(a.trace, 2);
@@ -423,10 +425,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t idesc = umma_idesc_f16(kBlockM, static_cast<uint32_t>(a.n_tile), a.fmt);
     int stage = 0;
     uint32_t phase = 0;
-    if (resident) {
-      mbar_wait(w_bar, 0);
-      tc_fence_after();
+    if (resident && elect_one()) {
+      // this CTA's weights: every (tap, k-block) slab of its N tile, once, grouped per (dt, dw) in MMA order so the
+      // first MMAs start after 3 * kblocks slabs, not after the whole filter.  Issued from this (otherwise idle) warp
+      // while warp 0 issues the activation loads, and BEFORE pdl_wait: weights do not depend on the previous kernel.
+      const uint32_t group_bytes = 3u * static_cast<uint32_t>(a.kblocks) * b_bytes;
+      for (int dti = 0; dti < a.ntd; ++dti)
+        for (int dwi = 0; dwi < 3; ++dwi) {
+          uint64_t* bar = &w_bar[dti * 3 + dwi];
+          mbar_expect_tx(bar, group_bytes);
+          for (int kb = 0; kb < a.kblocks; ++kb)
+            for (int dhi = 0; dhi < 3; ++dhi) {
+              const int tap = (dti * 3 + dhi) * 3 + dwi;
+              tma_load_2d(smem_w + static_cast<size_t>(tap * a.kblocks + kb) * b_bytes, &tmB, bar, kb * kBlockK,
+                          tap * a.Cout_pad + my_n * a.n_tile);
+            }
+        }
     }
+    __syncwarp();
+    pdl_wait();
     if (lane == 0) trace_mark(a.trace, 4);
     const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;   // SBO, version, swizzle mode
     const uint32_t desc_lo_flags = static_cast<uint32_t>(umma_desc_sw128(0));  // LBO field
@@ -481,6 +498,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int dwi = 0; dwi < 3; ++dwi) {
             // resident weights of tap (dti, dhi=0, dwi), k-block 0
             uint32_t wlo = desc_lo_flags | (w_lo + static_cast<uint32_t>(dti * 9 + dwi) * w_tap_step);
+            if (resident && local == 0) mbar_wait(&w_bar[dti * 3 + dwi], 0);  // this group's weight slabs have landed
             for (int kb = 0; kb < a.kblocks; ++kb, ++it, wlo += b_step) {
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
@@ -519,6 +537,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
+    pdl_wait();  // residuals / per-frame biases may be the previous kernel's output
     const int ewarp = warp - 2;
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read
     const int half = ewarp >> 2;           // which half of the accumulator columns
@@ -713,6 +732,11 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   a.ntaps = nt;
   a.bias = p->bias; a.rowbias = p->rowbias; a.rowbias_stride = p->rowbias_stride;
   a.rowscale = p->rowscale; a.rowscale_stride = p->rowscale_stride;
+  a.preadd = p->preadd; a.preadd_dtype = p->preadd_dtype; a.preadd_cstride = p->preadd_cstride;
+  if (p->preadd != nullptr)
+    FLAIR_REQUIRE(p->preadd_cstride >= p->Cout && (p->preadd_dtype == FLAIR_F32 || p->preadd_dtype == FLAIR_F16 ||
+                                                   p->preadd_dtype == FLAIR_BF16),
+                  "flair_conv_igemm: bad preadd geometry / dtype");
   a.residual = p->residual; a.residual_dtype = p->residual_dtype;
   a.residual_cstride = p->residual_cstride;
   a.residual2 = p->residual2; a.residual2_dtype = p->residual2_dtype;
@@ -780,12 +804,10 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
                   static_cast<int>(r));
   }
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static FlairPerDeviceOnce attr_once;
+  if (attr_once.first())
     FLAIR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
-    attr_set = true;
-  }
   const int total_tiles = a.m_tiles * a.n_tiles;
   int grid = flair_num_sms();
   if (grid > total_tiles) grid = total_tiles;

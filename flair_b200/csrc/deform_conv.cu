@@ -459,15 +459,14 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
 template <int VPG, bool BF16>
 cudaError_t launch_deform(int grid, size_t smem_bytes, cudaStream_t stream, const CUtensorMap& tmB, const CUtensorMap& tmOM,
                           const DeformArgs& a) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static FlairPerDeviceOnce attr_once;  // one per template instantiation
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(deform_conv_kernel<VPG, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
     if (e != cudaSuccess) return e;
     // ask for the smallest shared-memory carve-out that fits: the rest of the 256 KB stays L1 for the gather
     const int pct = static_cast<int>((smem_bytes + 2048) * 100 / (228 * 1024)) + 1;
     e = cudaFuncSetAttribute(deform_conv_kernel<VPG, BF16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   return flair_launch(deform_conv_kernel<VPG, BF16>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmB, tmOM, a);
 }

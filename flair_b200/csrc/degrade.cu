@@ -403,12 +403,10 @@ extern "C" int flair_blur_down_f32(const float* x, float* lr, const float* taps,
                 "flair_blur_down_f32: bad geometry k=%d sf=%d pre=%d H=%d W=%d", k, sf, pre, H, W);
   if (k == 9 && sf == 4) {  // the FLAIR blur operator (pseudoSR.py: 9 x 9 ds_kernel, factor 4)
     const size_t smem = sizeof(float) * (84 + static_cast<size_t>(16 * 4 + 8) * (64 * 4 + 8));
-    static bool attr = false;
-    if (!attr) {
+    static FlairPerDeviceOnce attr;
+    if (attr.first())
       FLAIR_CHECK_CUDA(cudaFuncSetAttribute(blur_down_tiled_kernel<9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
-      attr = true;
-    }
     dim3 grid(ceil_div(W / sf, 64), ceil_div(H / sf, 16), planes);
     FLAIR_CHECK_CUDA(flair_launch(blur_down_tiled_kernel<9, 4>, dim3(grid), dim3(256), smem, stream, x, lr, taps, pre, H, W));
     FLAIR_CHECK_LAUNCH();
@@ -433,12 +431,10 @@ extern "C" int flair_filter_same_f32(const float* x, const float* sub, float* ou
   if (k == 39) {  // the FLAIR inverse filter inv_hTh (pseudoSR.py:123-171)
     constexpr int K = 39, kpad = 40, pitch = (64 + K - 1 + 3) & ~3;
     const size_t smem = sizeof(float) * (K * kpad + static_cast<size_t>(16 + K - 1) * pitch);
-    static bool attr = false;
-    if (!attr) {
+    static FlairPerDeviceOnce attr;
+    if (attr.first())
       FLAIR_CHECK_CUDA(cudaFuncSetAttribute(filter_same_tiled_kernel<39>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
-      attr = true;
-    }
     dim3 grid(ceil_div(W, 64), ceil_div(H, 16), planes);
     FLAIR_CHECK_CUDA(flair_launch(filter_same_tiled_kernel<39>, dim3(grid), dim3(256), smem, stream, x, sub, out, taps, H, W));
     FLAIR_CHECK_LAUNCH();

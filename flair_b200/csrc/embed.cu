@@ -122,11 +122,9 @@ extern "C" int flair_linear_f32(const float* x, const float* Wt, const float* bi
   constexpr int MB = 16;
   const size_t smem = sizeof(float) * MB * K;
   FLAIR_REQUIRE(smem <= 96 * 1024, "flair_linear_f32: K=%d too large", K);
-  static bool attr = false;
-  if (!attr) {
+  static FlairPerDeviceOnce attr;
+  if (attr.first())
     FLAIR_CHECK_CUDA(cudaFuncSetAttribute(linear_f32_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
-  }
   FLAIR_CHECK_CUDA(flair_launch(linear_f32_kernel<MB>, dim3(ceil_div(N, 256)), dim3(256), smem, stream, x, Wt, bias, y, M, K, N, silu_in, silu_out));
   FLAIR_CHECK_LAUNCH();
   return 0;

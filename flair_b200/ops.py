@@ -55,7 +55,7 @@ def pack_conv_weight(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
 
 
 def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, rowscale=None, residual=None, residual2=None, out=None,
-         out_dtype=None, act=L.ACT_NONE, stride=1, nchw_out=False, out_scale=1.0, out2=None):
+         out_dtype=None, act=L.ACT_NONE, stride=1, nchw_out=False, out_scale=1.0, out2=None, preadd=None):
     """Implicit-GEMM convolution (see flair_conv_igemm in include/flair_b200.h).
 
     x: [B,T,H,W,Cin] channels-last 16-bit; wpk: pack_conv_weight(...) output."""
@@ -89,6 +89,11 @@ def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, rowscale=Non
         p.residual2 = _ptr(residual2)
         p.residual2_dtype = _DT[residual2.dtype]
         p.residual2_cstride = _cstride(residual2)
+    if preadd is not None:  # pre-activation addend (a partial convolution computed elsewhere), geometry of `out`
+        assert preadd.shape[-1] == cout and preadd.shape[:4].numel() == B * T * Ho * Wo
+        p.preadd = _ptr(preadd)
+        p.preadd_dtype = _DT[preadd.dtype]
+        p.preadd_cstride = _cstride(preadd)
     p.out = _ptr(out)
     p.out_dtype = _DT[out.dtype]
     p.out_layout = L.OUT_NCHW if nchw_out else L.OUT_NHWC
@@ -173,6 +178,9 @@ def dc_apply(x0, R, *, gamma=1.0, gamma_arr=None, clip_denoised=True):
     x0, R = _f32c(x0), _f32c(R)
     N, _, H, W = x0.shape
     out = torch.empty_like(x0)
+    if gamma_arr is not None:  # the kernel indexes gamma_arr[frame]: a stride-0 expand() view would read its neighbours
+        gamma_arr = _f32c(gamma_arr)
+        assert gamma_arr.numel() == N, "gamma_arr must hold one weight per frame"
     L.check(L.lib().flair_dc_apply_f32(_ptr(x0), _ptr(R), _ptr(gamma_arr), float(gamma), _ptr(out), N, H, W,
                                        int(clip_denoised), _stream()))
     return out

@@ -52,10 +52,12 @@ KNOBS = {
 class BlurRestore:
     """restore_fn of the gaussian / jpeg tasks (gaussian_restore, scripts/video_sample.py:183-193) bound to
     one window's degraded frames.  Callable like the reference closure; `fused_lr` lets the sampler
-    evaluate Up(.) inside its update kernel."""
+    evaluate Up(.) inside its update kernel.  InvhTh(y) is constant over the steps of a window and is
+    computed once here (the reference recomputes it at every step, pseudoSR.py:262-270)."""
 
-    def __init__(self, A, degraded, jpeg_qf=-1):
+    def __init__(self, A, degraded, jpeg_qf=-1, _inv=None):
         self.A, self.y, self.qf = A, degraded.reshape(-1, *degraded.shape[-3:]).contiguous(), jpeg_qf
+        self.inv_y = A.Conv_LR_with_Inv_hTh_OP(self.y) if _inv is None else _inv
 
     def _codec(self):
         if self.qf == -1:
@@ -69,8 +71,20 @@ class BlurRestore:
 
     def fused_lr(self, x):
         enc, dec = self._codec()
-        return (self.A.lr_correction(self.y, x, jpeg_decode=dec, jpeg_encode=enc),
+        return (self.A.lr_correction(None, x, jpeg_decode=dec, jpeg_encode=enc, inv_LR=self.inv_y),
                 self.A.Upscale_OP.Filter_OP.taps, int(self.A.ds_factor), int(self.A.pre_stride[0]))
+
+    # ---- static-buffer protocol of the graphed sampling step (guided_diffusion.gaussian_diffusion._StepGraph)
+    def signature(self):
+        return ("blur", id(self.A), self.qf, tuple(self.y.shape))
+
+    def static_clone(self):
+        """A copy bound to buffers the step graph owns; `load_from` refreshes them for the next window."""
+        return BlurRestore(self.A, self.y.clone(), self.qf, _inv=self.inv_y.clone())
+
+    def load_from(self, other):
+        self.y.copy_(other.y)
+        self.inv_y.copy_(other.inv_y)
 
 
 class BicubicRestore:
@@ -81,6 +95,15 @@ class BicubicRestore:
 
     def __call__(self, x):
         return self.A.restore(x, self.y)
+
+    def signature(self):
+        return ("bicubic", id(self.A), tuple(self.y.shape))
+
+    def static_clone(self):
+        return BicubicRestore(self.A, self.y.clone())
+
+    def load_from(self, other):
+        self.y.copy_(other.y)
 
 
 def init_frames(task, lr01, size):
@@ -126,9 +149,9 @@ def restore_window(model, diffusion, A, task, lr01, *, image_size, prev_recon=No
     for out in diffusion.p_sample_loop_progressive(
             model, noise.shape, noise=noise, model_kwargs=model_kwargs, device=dev, restore_fn=restore,
             aux_model=None, rho=knobs.rho, noise_level=knobs.noise_level, zeta=knobs.zeta, prev_recon=prev_recon,
-            t_start=t_start, noise_tape=tape, generator=generator):
+            t_start=t_start, noise_tape=tape, generator=generator, _views=True):
         final = out
-    return final["sample"]
+    return final["sample"].clone()  # the graphed step yields its static buffers: detach the result from them
 
 
 @torch.no_grad()

@@ -246,7 +246,7 @@ class GaussianDiffusion:
     def p_sample(self, model, x, t, clip_denoised=True, model_kwargs=None, restore_fn=None,
                  affine_matrices=None, face_restore_helper=None, aux_model=None, w=0.5, start_timestep=None,
                  tau=None, aligned=False, rho=0.35, prev_recon=None, gamma=None, _t_host=None, _noise=None,
-                 _generator=None):
+                 _generator=None, _coef=None):
         """x_t -> {sample: x_{t-1}, pred_xstart} (reference :423-517).
 
         restore_fn may be any callable Tensor->Tensor (protocol of :465-468); callables exposing
@@ -256,12 +256,14 @@ class GaussianDiffusion:
         if self.model_var_type not in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE) and model_out.shape[1] == 6:
             model_out = model_out[:, :3, ...]
         t64 = t.long()
-        coef = self._table(x.device, "update")
+        # _coef: update table with the gamma_t column already filled in (the graphed step indexes it by the
+        # device-resident t); otherwise gamma arrives per call like in the reference (:466)
+        coef = self._table(x.device, "update") if _coef is None else _coef
         gamma_arr = None
-        if restore_fn is not None:
+        if restore_fn is not None and _coef is None:
             if gamma is None:
                 raise AssertionError("restore_fn needs gamma (reference p_sample, :466)")
-            gamma_arr = gamma.reshape(gamma.shape[0], -1)[:, 0] if th.is_tensor(gamma) else \
+            gamma_arr = gamma.reshape(gamma.shape[0], -1)[:, 0].contiguous() if th.is_tensor(gamma) else \
                 th.full((x.shape[0],), float(gamma), device=x.device)
         noise = _noise if _noise is not None else (
             th.randn_like(x) if _generator is None else th.randn(x.shape, device=x.device, generator=_generator))
@@ -327,21 +329,23 @@ class GaussianDiffusion:
                 model, shape, noise=noise, clip_denoised=clip_denoised, model_kwargs=model_kwargs, device=device,
                 progress=progress, restore_fn=restore_fn, affine_matrices=affine_matrices,
                 face_restore_helper=face_restore_helper, aux_model=aux_model, w=w, tau=tau, aligned=aligned,
-                rho=rho, noise_level=noise_level, prev_recon=prev_recon, zeta=zeta, t_start=t_start):
+                rho=rho, noise_level=noise_level, prev_recon=prev_recon, zeta=zeta, t_start=t_start,
+                _views=post_fn is None):
             if post_fn is not None:
                 post_fn(out)
             final = out
-        return final["sample"]
+        return final["sample"].clone() if post_fn is None else final["sample"]
 
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, model_kwargs=None,
                                   device=None, progress=False, affine_matrices=None, face_restore_helper=None,
                                   aux_model=None, restore_fn=None, w=0.5, tau=None, aligned=False, rho=0.35,
                                   noise_level=None, prev_recon=None, zeta=-1, t_start=-1, noise_tape=None,
-                                  generator=None):
+                                  generator=None, _views=False):
         """Generator over per-step dicts {sample, pred_xstart, t} (reference :589-689).
 
         `noise_tape` / `generator` (optional, not in the reference) supply the per-step normals /
-        the torch generator they are drawn from: entry i is used by the i-th executed step (parity runs)."""
+        the torch generator they are drawn from: entry i is used by the i-th executed step (parity runs).
+        `_views=True` (internal): yield the graphed step's static output buffers without cloning them."""
         if device is None:
             device = next(model.parameters()).device
         if not isinstance(shape, (tuple, list, th.Size)):
@@ -366,6 +370,22 @@ class GaussianDiffusion:
             from tqdm.auto import tqdm
             indices = tqdm(indices)
         n = shape[0]
+        sg = None
+        if aux_model is None and _StepGraph.eligible(model, restore_fn, img):
+            sg = _StepGraph.get(self, model, img, model_kwargs or {}, restore_fn, prev_recon, gammas, rho,
+                                clip_denoised)
+        if sg is not None:
+            # One CUDA-graph replay per step: UNet forward, x0, data consistency and the fused update are a single
+            # graph (no host work between the ~3000 kernels of a step).  Yielded tensors are the graph's static
+            # buffers unless `_views` is False (they are overwritten by the next step).
+            with th.no_grad():
+                sg.load_window(img, model_kwargs or {}, restore_fn, prev_recon)
+                for step_no, i in enumerate(indices):
+                    out = sg.step(i, None if noise_tape is None else noise_tape[step_no], generator)
+                    if not _views:
+                        out = {k: v.clone() for k, v in out.items()}
+                    yield out
+            return
         with th.no_grad():
             for step_no, i in enumerate(indices):
                 t = th.full((n,), i, device=device, dtype=th.long)
@@ -378,6 +398,115 @@ class GaussianDiffusion:
                 img = out["sample"]
                 out["t"] = t
                 yield out
+
+
+class _StepGraph:
+    """One whole sampling step — `_WrappedModel` + UNet forward, x0 from eps, the task's data-consistency operator,
+    `prev_recon` overwrite and the rho-mixed update (reference p_sample, :423-517) — captured ONCE per signature into
+    a CUDA graph over static buffers and replayed per step.  The step index lives in a device tensor (the kernels index
+    their coefficient tables with it), the per-window inputs (conditioning frames, flows, degraded frames,
+    `prev_recon`) are copied into the static buffers when a window starts, and the graph's last node copies x_{t-1}
+    back into the x_t buffer, so a step costs the host one `fill_`, one `normal_` and one replay.
+    (FLAIR_STEP_GRAPH=0 falls back to one graph per UNet forward + eager update kernels.)"""
+
+    @staticmethod
+    def _unwrap(model):
+        return getattr(model, "model", model) if type(model).__name__ == "_WrappedModel" else model
+
+    @staticmethod
+    def eligible(model, restore_fn, img):
+        import os
+        m = _StepGraph._unwrap(model)
+        if os.environ.get("FLAIR_STEP_GRAPH", "1") == "0" or not img.is_cuda:
+            return False
+        if not (getattr(m, "use_cuda_graph", False) and hasattr(m, "_forward_impl") and hasattr(m, "flows_for")):
+            return False
+        return restore_fn is None or all(hasattr(restore_fn, a) for a in ("signature", "static_clone", "load_from"))
+
+    @staticmethod
+    def get(diffusion, model, img, kwargs, restore_fn, prev_recon, gammas, rho, clip_denoised):
+        m = _StepGraph._unwrap(model)
+        ksig = tuple(sorted((k, (tuple(v.shape), str(v.dtype)) if th.is_tensor(v) else
+                             (v if isinstance(v, (int, float, bool, str, type(None))) else id(v)))
+                            for k, v in kwargs.items() if not isinstance(v, np.ndarray)))
+        key = (id(m), m._param_stamp(), getattr(m, "compute_dtype", None), getattr(m, "stream_dtype", None),
+               tuple(img.shape), str(img.device), ksig, None if restore_fn is None else restore_fn.signature(),
+               None if prev_recon is None else tuple(prev_recon.shape), gammas.tobytes(), float(rho),
+               bool(clip_denoised))
+        cache = diffusion.__dict__.setdefault("_step_graphs", {})
+        sg = cache.get(key)
+        if sg is None:
+            if len(cache) >= 6:
+                cache.clear()
+            sg = cache[key] = _StepGraph(diffusion, model, img, kwargs, restore_fn, prev_recon, gammas, rho,
+                                         clip_denoised)
+        return sg
+
+    def __init__(self, diffusion, model, img, kwargs, restore_fn, prev_recon, gammas, rho, clip_denoised):
+        from flair_b200 import _lib as L
+        self.diffusion, self.model = diffusion, model
+        m = self._unwrap(model)
+        dev = img.device
+        self.x = img.float().clone()
+        self.noise = th.empty_like(self.x)
+        self.t = th.zeros(img.shape[0], dtype=th.long, device=dev)
+        self.kw = {k: (v.clone() if th.is_tensor(v) else v) for k, v in kwargs.items() if not isinstance(v, np.ndarray)}
+        self.frames = self.kw.get("num_frames")
+        fl = m.flows_for(self.x.shape, self.kw.get("low_res_input"), self.kw.get("rnn_input"), self.frames,
+                         self.kw.get("enable_cross_frames", True))
+        self.flows = {r: tuple(f.clone() for f in ff) for r, ff in fl.items()}
+        self.restore = None if restore_fn is None else restore_fn.static_clone()
+        self.prev = None if prev_recon is None else prev_recon.to(device=dev, dtype=th.float32).clone()
+        self.coef = diffusion._table(dev, "update", gammas)  # gamma_t in column 4; the reference keeps it
+        run_kw = dict(self.kw, _static_flows=self.flows)
+
+        def run():
+            out = diffusion.p_sample(model, self.x, self.t, clip_denoised=clip_denoised, model_kwargs=dict(run_kw),
+                                     restore_fn=self.restore, rho=rho, prev_recon=self.prev, _noise=self.noise,
+                                     _coef=self.coef)
+            return out
+
+        self.t.fill_(diffusion.num_timesteps - 1)
+        self.noise.normal_()
+        side = th.cuda.Stream()
+        side.wait_stream(th.cuda.current_stream())
+        with th.cuda.stream(side):  # warm-up: packs weights, sets kernel attributes, sizes the pool
+            run()
+        th.cuda.current_stream().wait_stream(side)
+        self.graph = th.cuda.CUDAGraph()
+        n0 = L.LAUNCHES[0]
+        with th.cuda.graph(self.graph):
+            self.out = run()
+            self.x.copy_(self.out["sample"])  # x_{t-1} becomes the next step's x_t inside the graph
+        self.launches = L.LAUNCHES[0] - n0
+        self.out["t"] = self.t
+
+    def load_window(self, img, kwargs, restore_fn, prev_recon):
+        m = self._unwrap(self.model)
+        self.x.copy_(img)
+        for k, v in kwargs.items():
+            if th.is_tensor(v):
+                self.kw[k].copy_(v)
+        fl = m.flows_for(self.x.shape, self.kw.get("low_res_input"), self.kw.get("rnn_input"), self.frames,
+                         self.kw.get("enable_cross_frames", True))
+        for r, ff in fl.items():
+            for dst, src in zip(self.flows[r], ff):
+                dst.copy_(src)
+        if restore_fn is not None:
+            self.restore.load_from(restore_fn)
+        if prev_recon is not None:
+            self.prev.copy_(prev_recon)
+
+    def step(self, i, noise, generator):
+        from flair_b200 import _lib as L
+        self.t.fill_(i)
+        if noise is not None:
+            self.noise.copy_(noise)
+        else:
+            self.noise.normal_(generator=generator)
+        self.graph.replay()
+        L.LAUNCHES[0] += self.launches
+        return self.out
 
 
 def _extract_into_tensor(arr, timesteps, broadcast_shape, dtype=th.float32):

@@ -129,12 +129,15 @@ class pseudoSR_PyTorch(nn.Module):
         self.pre_stride, self.post_stride = pre, post
 
     # -- fused entry used by the sampler: LR-domain correction q with R = Upscale_OP(q)
-    def lr_correction(self, LR, generated_image, jpeg_decode=None, jpeg_encode=None):
+    def lr_correction(self, LR, generated_image, jpeg_decode=None, jpeg_encode=None, inv_LR=None):
+        """q = InvhTh(codec(Down(x))) - InvhTh(LR).  `inv_LR` = InvhTh(LR) precomputed by the caller (constant
+        over the sampling steps of a window); else it is cached per LR tensor."""
         lr = self.DownscaleOP(generated_image)
         if jpeg_encode is not None and jpeg_decode is not None:
             lr = jpeg_decode(jpeg_encode(lr))
-        return ops.filter_same(lr, self.Conv_LR_with_Inv_hTh_OP.Filter_OP.taps, sub=None if LR is None else
-                               self._inv_of(LR))
+        if inv_LR is None and LR is not None:
+            inv_LR = self._inv_of(LR)
+        return ops.filter_same(lr, self.Conv_LR_with_Inv_hTh_OP.Filter_OP.taps, sub=inv_LR)
 
     def _inv_of(self, LR):
         """InvhTh(LR) — constant over the 100 steps of a window, so cached per LR tensor."""

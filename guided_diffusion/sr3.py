@@ -315,8 +315,14 @@ class UNet(nn.Module):
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
+    def flows_for(self, x_shape, low_res_input=None, rnn_input=None, num_frames=None, enable_cross_frames=True):
+        """The SPyNet flow pack a forward with these arguments uses ({} without BasicVSR++ levels); constant over the
+        sampling steps of a window."""
+        sizes = sorted({x_shape[-1] // s for s in self._vsr_strides()}) if enable_cross_frames else []
+        return self._flows(low_res_input if rnn_input is None else rnn_input, sizes) if sizes else {}
+
     def forward(self, x, timesteps, low_res_input=None, rnn_input=None, num_frames=None, enable_cross_frames=True,
-                vsrpp_weights=None, **kwargs):
+                vsrpp_weights=None, _static_flows=None, **kwargs):
         """x (B*T,3,H,W) fp32, timesteps = continuous noise level (B*T,) fp32 (respace.py:161-165),
         low_res_input (B,T,3,H,W) -> eps (B*T,out_channel,H,W) fp32."""
         if not x.is_cuda:
@@ -325,10 +331,8 @@ class UNet(nn.Module):
             raise NotImplementedError("FLAIR always conditions on low_res_input")
         T = int(num_frames)
         cross = bool(enable_cross_frames)
-        flows = {}
-        sizes = sorted({x.shape[-1] // s for s in self._vsr_strides()}) if cross else []
-        if sizes:
-            flows = self._flows(low_res_input if rnn_input is None else rnn_input, sizes)
+        flows = _static_flows if _static_flows is not None else \
+            self.flows_for(x.shape, low_res_input, rnn_input, T, cross)
         if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
             return self._forward_impl(x, timesteps, low_res_input, T, flows, cross, vsrpp_weights)
         from .unet_new import UNetModel

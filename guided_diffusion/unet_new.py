@@ -302,6 +302,11 @@ class TemporalAttention(nn.Module, _Packed):
         self.num_heads = num_heads if num_head_channels == -1 else channels // num_head_channels
         if num_frames % 2 != 1:
             raise AssertionError("num_frames must be odd")
+        if channels % self.num_heads != 0 or channels // self.num_heads != 64:
+            raise NotImplementedError("flair_attn_temporal is built for 64-channel heads (FLAIR: num_head_channels=64); "
+                                      f"got channels={channels}, heads={self.num_heads}")
+        if num_frames not in (5, 7):
+            raise NotImplementedError("flair_attn_temporal supports temporal windows of 5 (blur UNet) or 7 (SR3) frames")
         self.num_frames, self.num_head_channels, self.use_checkpoint = num_frames, num_head_channels, use_checkpoint
         self.qk_scale = (channels // num_heads) ** -0.5
         self.q_linear = linear(channels, channels)
@@ -364,7 +369,22 @@ class ResidualBlocksWithInputConv(nn.Module, _Packed):
 
     def _pack(self, dtype):
         blocks = [(_w(b.conv1, dtype), _f(b.conv1.bias), _w(b.conv2, dtype), _f(b.conv2.bias)) for b in self.main[2]]
-        return dict(w0=_w(self.main[0], dtype), b0=_f(self.main[0].bias), blocks=blocks)
+        w0 = self.main[0].weight.detach()
+        c = self.out_channels
+        pk = dict(w0=_w(self.main[0], dtype), b0=_f(self.main[0].bias), blocks=blocks)
+        if self.in_channels > c and self.in_channels % c == 0:
+            # input conv split by linearity: [static slices (known for all frames) | last slice (recurrent)]
+            pk["w0_static"] = ops.pack_conv_weight(w0[:, :-c], dtype)
+            pk["w0_last"] = ops.pack_conv_weight(w0[:, -c:], dtype)
+        return pk
+
+    def _tail(self, x, pk, c, extra_residual, out, out2):
+        for i, (w1, b1, w2, b2) in enumerate(pk["blocks"]):
+            last = i == len(pk["blocks"]) - 1
+            t = ops.conv(x, w1, c, (1, 3, 3), bias=b1, act=L.ACT_RELU)
+            x = ops.conv(t, w2, c, (1, 3, 3), bias=b2, residual=x, residual2=extra_residual if last else None,
+                         out=out if last else None, out2=out2 if last else None)
+        return x
 
     def run(self, feat, dtype, extra_residual=None, out=None, out2=None):
         """feat: [1,N,H,W,Cin] map.  Returns main(feat) (+ extra_residual fused into the last conv).
@@ -372,12 +392,21 @@ class ResidualBlocksWithInputConv(nn.Module, _Packed):
         pk = self.packed(dtype)
         c = self.out_channels
         x = ops.conv(feat, pk["w0"], c, (1, 3, 3), bias=pk["b0"], act=L.ACT_LRELU01)
-        for i, (w1, b1, w2, b2) in enumerate(pk["blocks"]):
-            last = i == len(pk["blocks"]) - 1
-            t = ops.conv(x, w1, c, (1, 3, 3), bias=b1, act=L.ACT_RELU)
-            x = ops.conv(t, w2, c, (1, 3, 3), bias=b2, residual=x, residual2=extra_residual if last else None,
-                         out=out if last else None, out2=out2 if last else None)
-        return x
+        return self._tail(x, pk, c, extra_residual, out, out2)
+
+    def static_part(self, feat_static, dtype):
+        """Input conv over the slices of the concat that are known for ALL frames before the recurrence starts
+        (reference :729-735: [feat_current | other branches]); batched over T, bias included, no activation."""
+        pk = self.packed(dtype)
+        return ops.conv(feat_static, pk["w0_static"], self.out_channels, (1, 3, 3), bias=pk["b0"])
+
+    def run_split(self, last_slice, static_part, dtype, extra_residual=None, out=None, out2=None):
+        """main(cat(static slices, last_slice)) with the static slices' share of the input conv precomputed
+        (`static_part`): the recurrent launch contracts K = C instead of 2C / 3C."""
+        pk = self.packed(dtype)
+        c = self.out_channels
+        x = ops.conv(last_slice, pk["w0_last"], c, (1, 3, 3), preadd=static_part, act=L.ACT_LRELU01)
+        return self._tail(x, pk, c, extra_residual, out, out2)
 
 
 class ModulatedDeformConv2d(nn.Module):
@@ -412,6 +441,7 @@ class SecondOrderDeformableAlignment(ModulatedDeformConv2d, _Packed):
 
     def _pack(self, dtype):
         co = self.conv_offset
+        oc = self.out_channels
         # deformable weight (C, 2C, 3, 3) -> 1x1 GEMM weight over K = tap*2C + ci
         wd = self.weight.detach().float().permute(0, 2, 3, 1).reshape(self.out_channels, -1)
         off = [(_w(co[i], dtype), _f(co[i].bias)) for i in (0, 2, 4)]
@@ -420,20 +450,37 @@ class SecondOrderDeformableAlignment(ModulatedDeformConv2d, _Packed):
             perm = ops.deform_offset_perm(self.deform_groups).to(w6.device)
             w6, b6 = w6[perm], b6[perm]
         off.append((ops.pack_conv_weight(w6, dtype), b6.float().contiguous()))
-        return dict(off=off, wd=ops.pack_conv_weight(wd, dtype), bd=_f(self.bias))
+        # first offset conv split by linearity over its input slices [warp(prop) | cur | warp(prev2) | f1 f2]
+        # (reference :874-879): the `cur` and flow slices are known for all frames up front
+        w0 = co[0].weight.detach()
+        split = dict(rec2=ops.pack_conv_weight(th.cat([w0[:, :oc], w0[:, 2 * oc:3 * oc]], 1), dtype),
+                     rec1=ops.pack_conv_weight(w0[:, :oc], dtype),
+                     static=ops.pack_conv_weight(th.cat([w0[:, oc:2 * oc], w0[:, 3 * oc:]], 1), dtype))
+        return dict(off=off, wd=ops.pack_conv_weight(wd, dtype), bd=_f(self.bias), split=split)
 
     @property
     def fused(self):
         """One-launch gather + tcgen05 GEMM (flair_deform_conv): the FLAIR shapes (16 deform groups, C = 64 / 128)."""
         return self.deform_groups == 16 and self.out_channels in (64, 128)
 
-    def run(self, xa, xb, cond, flow_1, flow_2, dtype, out, xa_g=None, xb_g=None):
-        """xa/xb: [N,H,W,C] (feat_prop, feat_n2), xa_g/xb_g their pair-plane copies [8][N*H*W][2][C/8];
-        cond: [1,N,H,W,3C+4(+pad)] offset-net input."""
+    def static_part(self, cur_flows, dtype):
+        """conv_offset[0] over the [cur | f1 f2] slices of its input for ALL frames (bias included, no activation)."""
+        pk = self.packed(dtype)
+        return ops.conv(cur_flows, pk["split"]["static"], self.out_channels, (1, 3, 3), bias=pk["off"][0][1])
+
+    def run(self, xa, xb, cond, flow_1, flow_2, dtype, out, xa_g=None, xb_g=None, static_part=None):
+        """xa/xb: [N,H,W,C] (feat_prop, feat_n2), xa_g/xb_g their pair-plane copies [8][N*H*W][2][C/8].
+        cond: with `static_part` (the precomputed [cur | flows] share of conv_offset[0], [1,N,H,W,C]) the warped
+        features only: [1,N,H,W,2C] = [warp(prop) | warp(prev2)] or [1,N,H,W,C] = [warp(prop)] (first-order step);
+        without it the full offset-net input [1,N,H,W,3C+4]."""
         pk = self.packed(dtype)
         oc = self.out_channels
-        o = cond
-        for i, (w, b) in enumerate(pk["off"][:3]):
+        if static_part is not None:
+            w0 = pk["split"]["rec2" if cond.shape[-1] == 2 * oc else "rec1"]
+            o = ops.conv(cond, w0, oc, (1, 3, 3), preadd=static_part, act=L.ACT_LRELU01)
+        else:
+            o = ops.conv(cond, pk["off"][0][0], oc, (1, 3, 3), bias=pk["off"][0][1], act=L.ACT_LRELU01)
+        for i, (w, b) in enumerate(pk["off"][1:3]):
             o = ops.conv(o, w, oc, (1, 3, 3), bias=b, act=L.ACT_LRELU01)
         w, b = pk["off"][3]
         om = ops.conv(o, w, 27 * self.deform_groups, (1, 3, 3), bias=b, out_dtype=th.float16)
@@ -495,53 +542,55 @@ class BasicVSRPP(nn.Module, _Packed):
             wmap8 = wmap[:, None].expand(T, 8, H, W).contiguous()
             wmap8n = th.roll(wmap.reshape(T, H * W), -1, 1).reshape(T, 1, H, W).expand(T, 8, H, W).contiguous()
         frames = hidden[0]  # [T,H,W,C]
-        cpad = (3 * C + 4 + 7) // 8 * 8
         # reconstruction input for ALL frames: [spatial | backward feature | forward feature]; the two
         # propagation passes write their outputs straight into its channel slices
         rec_cat = th.empty(1, T, H, W, 3 * C, dtype=dt, device=dev)
         ops.copy_channels_into(frames[None], rec_cat, 0)
+        # [cur | f1 f2] per direction: the non-recurrent slices of the offset net's input
+        cf = C + 8  # C + 4 flow channels, channel stride padded to a multiple of 8 (the pad is never read)
         for name in ("backward_1", "forward_1"):
             fwd = name == "forward_1"
             so = 2 * C if fwd else C
             order = list(range(T)) if fwd else list(range(T - 1, -1, -1))
-            # per-frame inputs that do not depend on the recurrence, written once for all frames
-            cond_all = th.empty(1, T, H, W, cpad, dtype=dt, device=dev)     # [warp(prop) | cur | warp(prev2) | f1 f2]
-            ops.copy_channels_into(frames[None], cond_all, C)
-            ops.planes_to_cl(f12[name], cond_all[0], 3 * C)
-            cat_all = th.empty(1, T, H, W, (3 if fwd else 2) * C, dtype=dt, device=dev)  # [cur | (backward) | aligned]
-            ops.copy_channels_into(frames[None], cat_all, 0)
-            if fwd:
-                ops.copy_channels_into(rec_cat[..., C:2 * C], cat_all, C)
-            ao = (2 if fwd else 1) * C
+            da, bb = self.deform_align[name], self.backbone[name]
+            # ---- everything that does not depend on the recurrence, once for all T frames (batched launches):
+            # a convolution is linear in the channel slices of its input, so the `cur` / flow slices of the first
+            # offset conv (reference :874-879) and the `cur` (+ backward) slices of the backbone's first conv
+            # (:729-735) are convolved here and enter the per-frame launches as a pre-activation addend.
+            cur_fl = th.empty(1, T, H, W, cf, dtype=dt, device=dev)
+            ops.copy_channels_into(frames[None], cur_fl, 0)
+            ops.planes_to_cl(f12[name], cur_fl[0], C)
+            p_off = da.static_part(cur_fl[..., :C + 4], ctx.dtype)                 # [1,T,H,W,C]
+            p_bb = bb.static_part(rec_cat[..., :so], ctx.dtype)                    # [1,T,H,W,C]
+            warps = th.empty(1, T, H, W, 2 * C, dtype=dt, device=dev)              # [warp(prop) | warp(prev2)]
+            aligned_all = th.empty(1, T, H, W, C, dtype=dt, device=dev)
             prop = prev2 = prop_g = prev2_g = None
-            fused = self.deform_align[name].fused
+            fused = da.fused
             # pair-plane copies of the propagated features (written by the backbone's last conv): the layout the
-            # fused deformable conv gathers from; slot 1 of each plane's last entry is never written -> keep it finite
-            gm_all = None
-            if fused:
-                gm_all = th.empty(T, 8, H * W, 2, C // 8, dtype=dt, device=dev)
-                gm_all[:, :, -1, 1].zero_()
+            # fused deformable conv gathers from; slot 1 of each plane's last entry is never written -> the buffer
+            # is persistent and zeroed once (it is read with weight 0, it only has to stay finite)
+            gm_all = self._persistent(("gm", name, T, H, W, C, dt, str(dev)),
+                                      lambda: th.zeros(T, 8, H * W, 2, C // 8, dtype=dt, device=dev)) if fused else None
             for i, idx in enumerate(order):
-                aligned = cat_all[0, idx:idx + 1, :, :, ao:ao + C]  # [1,H,W,C] slice: deform output / zeros
                 if i == 0:
-                    aligned.zero_()
+                    aligned = self._zeros(aligned_all[0, :1])  # [1,H,W,C] of zeros (cached)
                 else:
-                    cond = cond_all[0, idx:idx + 1]
+                    aligned = aligned_all[0, idx:idx + 1]
+                    wb = warps[:, idx:idx + 1]
                     f1, f2 = f12[name][idx:idx + 1, 0:2], f12[name][idx:idx + 1, 2:4]
                     if i > 1:
-                        ops.flow_warp2(prop, f1, cond[..., :C], prev2, f2, cond[..., 2 * C:3 * C])
-                        xb, xb_g = prev2, prev2_g
-                    else:
-                        ops.flow_warp(prop, f1, out=cond[..., :C])
-                        cond[..., 2 * C:3 * C].zero_()
-                        xb = self._zeros(prop)
+                        ops.flow_warp2(prop, f1, wb[0, ..., :C], prev2, f2, wb[0, ..., C:])
+                        cond, xb, xb_g = wb, prev2, prev2_g
+                    else:  # first-order step: the second-order slices are zeros -> contract K = C only
+                        ops.flow_warp(prop, f1, out=wb[0, ..., :C])
+                        cond, xb = wb[..., :C], self._zeros(prop)
                         xb_g = self._zeros(gm_all[0]) if fused else None
-                    self.deform_align[name].run(prop, xb, cond[None, ..., : 3 * C + 4], f1, f2, ctx.dtype,
-                                                out=aligned[None], xa_g=prop_g, xb_g=xb_g)
+                    da.run(prop, xb, cond, f1, f2, ctx.dtype, out=aligned[None], xa_g=prop_g, xb_g=xb_g,
+                           static_part=p_off[:, idx:idx + 1])
                 new = rec_cat[0, idx:idx + 1, :, :, so:so + C]
                 new_g = gm_all[idx] if fused else None
-                self.backbone[name].run(cat_all[:, idx:idx + 1], ctx.dtype, extra_residual=aligned[None], out=new[None],
-                                        out2=new_g)
+                bb.run_split(aligned[None], p_bb[:, idx:idx + 1], ctx.dtype, extra_residual=aligned[None], out=new[None],
+                             out2=new_g)
                 if wmap is not None:
                     ops.scale_pixels_(new, wmap[idx:idx + 1])
                     if fused:  # slot 0 of entry p is pixel p, slot 1 is pixel p+1
@@ -553,6 +602,14 @@ class BasicVSRPP(nn.Module, _Packed):
         rec = self.reconstruction.run(rec_cat, ctx.dtype)
         return ops.conv(rec, pk_last[0], C, (1, 1, 1), bias=pk_last[1], residual=stream, rowscale=gate,
                         out_dtype=stream.dtype)
+
+    def _persistent(self, key, make):
+        """Module-owned buffers that outlive a forward (allocated during the eager warm-up that precedes every
+        CUDA-graph capture, so captured graphs see stable addresses and no fill kernels)."""
+        bufs = self.__dict__.setdefault("_persist_bufs", {})
+        if key not in bufs:  # never evicted: captured graphs hold these addresses
+            bufs[key] = make()
+        return bufs[key]
 
     def _zeros(self, like):
         bufs = self.__dict__.setdefault("_zero_bufs", {})
@@ -820,8 +877,15 @@ class UNetModel(nn.Module):
 
     # ------------------------------------------------------------------ forward
     @th.no_grad()
+    def flows_for(self, x_shape, low_res_input=None, rnn_input=None, num_frames=None, enable_cross_frames=True):
+        """The SPyNet flow pack a forward with these arguments uses ({} when no BasicVSR++ module runs).  Depends on
+        `rnn_input` / `low_res_input` only, i.e. it is constant over the sampling steps of a window."""
+        if enable_cross_frames and self.need_flows_res and any(isinstance(m, BasicVSRPP) for m in self.modules()):
+            return self._flows(low_res_input if rnn_input is None else rnn_input, int(num_frames))
+        return {}
+
     def forward(self, x, timesteps, low_res_input=None, num_frames=None, rnn_input=None, enable_cross_frames=True,
-                vsrpp_weights=None, **kwargs):
+                vsrpp_weights=None, _static_flows=None, **kwargs):
         """x (B*T,3,H,W) fp32, timesteps (B*T,), low_res_input (B,T,3,H,W) -> (B*T,out_channels,H,W) fp32.
 
         With `use_cuda_graph` (default) the ~5000 kernel launches of one forward are captured once per
@@ -831,9 +895,9 @@ class UNetModel(nn.Module):
             raise RuntimeError("guided_diffusion.unet_new.UNetModel runs on a B200 only (no CPU fallback)")
         T = int(num_frames)
         cross = bool(enable_cross_frames)
-        flows = {}
-        if cross and self.need_flows_res and any(isinstance(m, BasicVSRPP) for m in self.modules()):
-            flows = self._flows(low_res_input if rnn_input is None else rnn_input, T)
+        # _static_flows: flow pack precomputed by the caller (the graphed sampling step keeps it in static buffers)
+        flows = _static_flows if _static_flows is not None else \
+            self.flows_for(x.shape, low_res_input, rnn_input, T, cross)
         if not self.use_cuda_graph or th.cuda.is_current_stream_capturing():
             return self._forward_impl(x, timesteps, low_res_input, T, flows, cross, vsrpp_weights)
         return self._forward_graphed(x, timesteps, low_res_input, T, flows, cross, vsrpp_weights)

@@ -57,7 +57,7 @@ int flair_check_device(int dev);
  * sr3.py:95,104,120,146; unet.py conv (3,1,1); mmedit conv3x3 inside
  * BasicVSR++ (unet_new.py:659-668,859-867).
  *
- *   out[b,t,h,w,n] = act( bias[n] + rowbias[b*T+t, n]
+ *   out[b,t,h,w,n] = act( bias[n] + rowbias[b*T+t, n] + preadd[b,t,h,w,n]
  *                         + sum_{taps,c} x[b,t+dt,h*sh+dh,w*sw+dw,c] * wgt[tap][n][c] )
  *                    * out_scale * rowscale[b*T+t, n]  (+ residual (+ residual2))
  *
@@ -103,6 +103,16 @@ typedef struct flair_conv_params {
   void* out2;
   int out2_group_channels;       /* 8 or 16                                   */
   long long out2_group_stride;   /* elements between group planes             */
+  /* optional pre-activation addend with the geometry of `out` (NHWC):        */
+  /*   out = act(bias + rowbias + preadd + conv(x)) ...                       */
+  /* A convolution over a channel concat is linear in its input slices, so    */
+  /* the slices known for all frames up front (BasicVSR++: the current frame  */
+  /* and the flows in the offset net, unet_new.py:874-879; the spatial and    */
+  /* backward features in the backbone input, :729-735) are convolved once,   */
+  /* batched over T, and enter the per-frame recurrent launch here.           */
+  const void* preadd;
+  int preadd_dtype;    /* FLAIR_BF16 / FLAIR_F32 / FLAIR_F16                  */
+  int preadd_cstride;
 } flair_conv_params;
 
 int flair_conv_igemm(const flair_conv_params* p, void* stream);

@@ -56,3 +56,18 @@ def test_sr3_video_mode(sr3_oracle):
     out = m.forward(fx["x"], fx["video_level"], fx["low_res"][None], num_frames=4, enable_cross_frames=True,
                     vsrpp_weights=fx["vsrpp_weights"])
     assert rel_err(out, fx["video_out"]) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ TemporalAttention
+@pytest.mark.parametrize("name", ["f5", "f7"])
+def test_temporal_attention_isolated(golden, name):
+    """oracle.temporal_attention against the reference modules in isolation (unet_new.TemporalAttention F=5,
+    unet.TemporalAttention F=7) on T=9 frames: interior frames with F-1 distinct neighbours + both padded ends
+    (tests/golden/temporal_attention.pt, tools/gen_golden_big.py tattn)."""
+    fx = golden("temporal_attention.pt")
+    sd = {"ta." + k: v for k, v in fx[name]["sd"].items()}
+    m = BlurUNetOracle.__new__(BlurUNetOracle)
+    m.sd, m.heads_dim = sd, 64
+    m.p = lambda n: sd[n].float()
+    out = m.temporal_attention(fx["x"], "ta", frames=fx[name]["frames"])
+    assert rel_err(out, fx[name]["out"]) < 2e-5
