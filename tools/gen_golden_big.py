@@ -214,8 +214,46 @@ def tattn():
     torch.save(fx, OUT / "temporal_attention.pt")
 
 
+def script_meta():
+    """The reference demo script's constants / config dictionaries and, for both model families as the script builds
+    them (MODEL_TYPE[task](**MODEL_CONFIG[task]) followed by convert_to_fp16(), scripts/video_sample.py:327-330),
+    the checkpoint layout a `torch.load`-ed state dict must have: key -> (shape, dtype)."""
+    import importlib
+    import json
+    sys.path.insert(0, "/root/reference/scripts")
+    m = importlib.import_module("scripts.video_sample")
+
+    def plain(v):
+        if isinstance(v, dict):
+            return {k: plain(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return [plain(x) for x in v]
+        if isinstance(v, (int, float, str, bool, type(None))):
+            return v
+        return str(v)
+
+    meta = {"FRAME_SLICE_LEN": m.FRAME_SLICE_LEN, "OVERLAP": m.OVERLAP, "DEFAULT_WEIGHT": m.DEFAULT_WEIGHT,
+            "CKPT_PATH": plain(m.CKPT_PATH), "DIFFUSION_CONFIG": plain(m.DIFFUSION_CONFIG),
+            "MODEL_CONFIG": plain(m.MODEL_CONFIG), "MODEL_TYPE": {k: v.__module__ + "." + v.__name__ for k, v in m.MODEL_TYPE.items()},
+            "RESTORE_FUNC": {k: v.__name__ for k, v in m.RESTORE_FUNC.items()},
+            "commands": sorted(n for n in dir(m) if n.endswith("_demo")), "checkpoint_layout": {}}
+    import inspect
+    sig = inspect.signature(m.main)
+    meta["main_signature"] = {k: (None if p.default is inspect._empty else plain(p.default)) for k, p in sig.parameters.items()}
+    for task in ("gaussian", "x8_bicubic"):
+        model = _with_cuda_flag(lambda: m.MODEL_TYPE[task](**m.MODEL_CONFIG[task]))
+        model.convert_to_fp16()
+        meta["checkpoint_layout"][task] = {k: [list(v.shape), str(v.dtype)] for k, v in model.state_dict().items()}
+        print(task, len(meta["checkpoint_layout"][task]), "state-dict entries")
+        del model
+    (OUT / "script_meta.json").write_text(json.dumps(meta, indent=0))
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "script":
+        script_meta()
+        raise SystemExit(0)
     if what == "blur256":
         blur256()
     elif what == "sr3_256":
