@@ -129,7 +129,7 @@ def cpu_config1_factory():
     keys = _blur_unet_keys(cfg)
     sd = {k: synth.synthetic_tensor(k, shp, 1234) for k, shp in keys.items()}
     model = BlurUNetOracle(cfg, sd)
-    taps = torch.load(ROOT / "tests" / "golden" / "pseudosr_taps.pt", map_location="cpu", weights_only=False)
+    taps = torch.load(ROOT / "tests" / "golden" / "pseudosr_taps.pt", map_location="cpu", weights_only=True)
     ds, inv = taps["ds_kernel"].float(), taps["inv_hTh"].float()
     tab = Tables("face_blur", 1000)
     hr = synth.synthetic_clip(1, SIZE, seed=1) * 2 - 1
@@ -178,7 +178,7 @@ def reference_video_note():
     fixture was generated in the build container (tools/gen_golden_big.py blur256): context only."""
     p = ROOT / "tests" / "golden" / "unet_blur_256.pt"
     try:
-        fx = torch.load(p, map_location="cpu", weights_only=False)
+        fx = torch.load(p, map_location="cpu", weights_only=True)
         return {"reference_video_forward_T10_256_cpu_s": round(float(fx["cpu_seconds"]), 1), "cores": int(fx["cores"]),
                 "where": "build container, tools/gen_golden_big.py blur256 (unmodified /root/reference)"}
     except Exception:

@@ -119,9 +119,18 @@ def main(task, video_path, output_path, device=torch.device("cuda"), t_start=-1,
         from flair_b200 import synth
         model.load_state_dict(synth.synthetic_state_dict(model))
     else:
-        model.load_state_dict(torch.load(CKPT_PATH[task], map_location="cpu"))
-    if w != 1.0 and not os.path.exists(CKPT_PATH["codeformer"]):
-        print("codeformer checkpoint not found: running without the auxiliary face prior (aux_model=None)")
+        # checkpoints are plain state dicts: refuse arbitrary pickles
+        model.load_state_dict(torch.load(CKPT_PATH[task], map_location="cpu", weights_only=True))
+    # The auxiliary face prior (CodeFormer + facelib crops, reference :350-360,446-456) is reference PyTorch outside
+    # this repo's scope (BASELINE.json north_star); this script always samples with aux_model=None, so `w`, `tau`
+    # and `aligned` have no effect here.  guided_diffusion.gaussian_diffusion.p_sample keeps the reference's
+    # aux-prior branch (tests/test_gpu_round2.py::test_p_sample_aux_branch_vs_oracle): pass `aux_model=` to
+    # SpacedDiffusion.sample() to use a prior of your own.
+    print("auxiliary face prior (CodeFormer) is not part of this build: sampling with aux_model=None "
+          f"(w={w}, tau={tau}, aligned={aligned} are ignored)")
+    if task in ("x8_bicubic", "x16_bicubic"):
+        print("face-parse background weights (facelib BiSeNet, reference :427-444) are not part of this build: "
+              f"vsrpp_weights={DEFAULT_WEIGHT}")
     frames = _read_frames(video_path).to(device)
     A_func = get_A_func(task, device, image_size)
     knobs = pipeline.TaskKnobs(rho=rho, noise_level=noise_level, zeta=zeta, jpeg_qf=jpeg_qf,

@@ -20,7 +20,7 @@ def golden():
 
     def load(name):
         if name not in cache:
-            cache[name] = torch.load(GOLDEN / name, map_location="cpu", weights_only=False)
+            cache[name] = torch.load(GOLDEN / name, map_location="cpu", weights_only=True)
         return cache[name]
 
     return load

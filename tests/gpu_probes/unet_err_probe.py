@@ -5,7 +5,7 @@ sys.path.insert(0, "."); sys.path.insert(0, "tests")
 from flair_b200 import synth
 from guided_diffusion.unet_new import UNetModel
 
-fx = torch.load("tests/golden/unet_blur.pt", weights_only=False)
+fx = torch.load("tests/golden/unet_blur.pt", weights_only=True)
 model = UNetModel(**fx["cfg"], use_fp16=True, use_checkpoint=True)
 model.load_state_dict({k: synth.synthetic_tensor(k, shp, 1234) for k, shp in fx["keys"].items()})
 model.convert_to_fp16(); model.eval().cuda()

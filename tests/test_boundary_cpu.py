@@ -160,3 +160,68 @@ def test_deform_offset_permutation_and_pair_planes():
     assert torch.equal(P[:, :, 0], flat.permute(1, 0, 2))                    # slot 0: pixel p
     assert torch.equal(P[:, :-1, 1], flat.permute(1, 0, 2)[:, 1:])           # slot 1: pixel p+1 (row-major, across rows/images)
     assert float(P[:, -1, 1].abs().max()) == 0.0                             # last entry: zeros
+
+
+# ------------------------------------------------------------------------------------------------ demo script (f1 / f4)
+def _script():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("flair_video_sample", ROOT / "scripts" / "video_sample.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_demo_script_matches_reference_constants():
+    """scripts/video_sample.py exposes the reference script's names, constants and configuration dictionaries
+    (tests/golden/script_meta.json was dumped from the UNMODIFIED /root/reference/scripts/video_sample.py by
+    tools/gen_golden_big.py script)."""
+    import json
+    ref = json.loads((ROOT / "tests" / "golden" / "script_meta.json").read_text())
+    m = _script()
+    assert m.FRAME_SLICE_LEN == ref["FRAME_SLICE_LEN"] and m.OVERLAP == ref["OVERLAP"]
+    assert m.DEFAULT_WEIGHT == ref["DEFAULT_WEIGHT"] and m.CKPT_PATH == ref["CKPT_PATH"]
+    for task, cfg in ref["DIFFUSION_CONFIG"].items():
+        mine = m.DIFFUSION_CONFIG[task]
+        assert set(mine) == set(cfg), task
+        for k, v in cfg.items():
+            assert (mine[k] == v) or (str(mine[k]) == v), (task, k, mine[k], v)   # enums are dumped as str()
+    for task, cfg in ref["MODEL_CONFIG"].items():
+        mine = m.MODEL_CONFIG[task]
+        assert set(mine) == set(cfg), (task, set(mine) ^ set(cfg))
+        for k, v in cfg.items():
+            got = list(mine[k]) if isinstance(mine[k], tuple) else mine[k]
+            assert got == v or str(mine[k]) == v, (task, k, mine[k], v)
+    assert {k: v.__name__ for k, v in m.RESTORE_FUNC.items()} == ref["RESTORE_FUNC"]
+    assert {k: v.__name__ for k, v in m.MODEL_TYPE.items()} == {k: v.rsplit(".", 1)[1] for k, v in ref["MODEL_TYPE"].items()}
+    for name in ref["commands"]:
+        assert callable(getattr(m, name)), name
+    import inspect
+    mine_sig = inspect.signature(m.main).parameters
+    for k, default in ref["main_signature"].items():
+        assert k in mine_sig, k
+        if default is not None and k != "device":
+            assert mine_sig[k].default == default, (k, mine_sig[k].default, default)
+
+
+@pytest.mark.parametrize("task,ref_task", [("face_blur", "gaussian"), ("face_bicubic", "x8_bicubic")])
+def test_checkpoint_layout_after_convert_to_fp16(task, ref_task):
+    """f4: a reference checkpoint is `torch.load`-ed into the model AFTER convert_to_fp16() (reference
+    scripts/video_sample.py:327-330).  The models `create_model_and_diffusion` builds must then expose exactly the
+    reference's state-dict keys, shapes AND dtypes (fp16 torso convs, fp32 norms / embeddings / SPyNet), so a
+    strict load of a reference-format checkpoint neither fails nor casts."""
+    import json
+    from guided_diffusion.script_util import create_model_and_diffusion
+    ref = json.loads((ROOT / "tests" / "golden" / "script_meta.json").read_text())["checkpoint_layout"][ref_task]
+    model, diffusion = create_model_and_diffusion(task, 512)
+    model.convert_to_fp16()
+    sd = model.state_dict()
+    assert set(sd) == set(ref), sorted(set(sd) ^ set(ref))[:8]
+    bad = [(k, tuple(v.shape), str(v.dtype), ref[k]) for k, v in sd.items()
+           if list(v.shape) != ref[k][0] or str(v.dtype) != ref[k][1]]
+    assert not bad, bad[:8]
+    # a checkpoint in the reference format (values do not matter here) loads strictly and bit-exactly
+    ckpt = {k: torch.full(shape, 0.5, dtype=getattr(torch, dt.split(".")[1])) for k, (shape, dt) in ref.items()}
+    model.load_state_dict(ckpt, strict=True)
+    k0 = next(k for k, (s, dt) in ref.items() if dt == "torch.float16")
+    assert model.state_dict()[k0].dtype == torch.float16 and float(model.state_dict()[k0].flatten()[0]) == 0.5
+    assert diffusion.num_timesteps == 100

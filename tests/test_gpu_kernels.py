@@ -39,7 +39,13 @@ CONV_CASES = [
     (1, 3, 16, 16, 64, 64, (3, 1, 1), 1, None, False, torch.float16, False),       # sr3 temporal (3,1,1)
     (1, 2, 32, 32, 64, 128, (1, 3, 3), 2, None, False, torch.float16, False),      # sr3 Downsample: stride 2
     (1, 3, 24, 40, 64, 64, (1, 3, 3), 1, "relu", True, torch.float16, False),      # ragged map (partial tiles)
-    (1, 4, 64, 64, 128, 128, (1, 3, 3), 1, None, False, torch.bfloat16, False),    # halo tiles + resident weights
+    (1, 4, 64, 64, 128, 128, (1, 3, 3), 1, None, False, torch.bfloat16, False),    # halo tiles, streamed weight ring
+    (1, 1, 256, 256, 64, 64, (1, 3, 3), 1, "lrelu", True, torch.float16, False),   # halo, resident, 4 tiles per CTA
+    (1, 1, 128, 128, 128, 128, (1, 3, 3), 1, "relu", False, torch.float16, False), # halo, streamed, one tile per CTA
+    (1, 2, 48, 24, 68, 64, (1, 3, 3), 1, None, False, torch.float16, False),       # [cur | flows]: Cin = C + 4, ragged
+    (1, 4, 32, 16, 128, 64, (3, 3, 3), 1, None, True, torch.float16, False),       # conv3d halo: 27 taps streamed
+    (1, 3, 16, 8, 256, 256, (1, 3, 3), 1, "silu", False, torch.float16, False),    # halo at the minimum map, N = 256 / split
+    (1, 10, 16, 16, 512, 512, (1, 3, 3), 1, None, False, torch.float16, False),    # low-res: N tile split for parallelism
 ]
 
 
