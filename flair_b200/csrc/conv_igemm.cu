@@ -91,6 +91,7 @@ struct ConvKArgs {
   uint32_t fmt;
   float* gn_partial;
   int gn_groups;
+  int pf_ok;               // 16-bit addends are 16-byte aligned with channel strides % 8 == 0 (prefetchable as uint4)
   uint16_t* out2;          // optional copy of a 16-bit NHWC output as pair planes [Cout/out2_gs][pixels][2][out2_gs]:
   int out2_gs;             // entry p = (pixel p, pixel p+1), the source layout of flair_deform_conv
   long long out2_gstride;  // elements between group planes
@@ -172,6 +173,20 @@ __device__ __forceinline__ void add_residual(float (&v)[16], const void* base, i
   }
 }
 
+// v[j] += the 16 prefetched 16-bit values of one chunk (two 16-byte vectors)
+__device__ __forceinline__ void add_prefetched(float (&v)[16], const uint4 (&u2)[2], int dtype) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint32_t uu[4] = {u2[q].x, u2[q].y, u2[q].z, u2[q].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack16(uu[e], dtype);
+      v[8 * q + 2 * e] += f.x;
+      v[8 * q + 2 * e + 1] += f.y;
+    }
+  }
+}
+
 struct EpiPos {
   int w, h, n0;
   bool valid;
@@ -182,9 +197,12 @@ struct EpiPos {
 // KIND: 0 fp16 NHWC, 1 bf16 NHWC, 2 fp32 NHWC, 3 fp32 NCHW.  ACT: FLAIR_ACT_*.
 // One 16-column chunk of one epilogue warp: bias, per-frame bias, activation, gate, residuals, store.
 // KIND: 0 fp16 NHWC, 1 bf16 NHWC, 2 fp32 NHWC, 3 fp32 NCHW.  ACT: FLAIR_ACT_*.
+// pfmask: addends already in registers (loaded while the MMAs of the tile were still running): bit 0 = preadd in
+// pfA, bit 1 = residual in pfB, bit 2 = residual2 in pfA.
 template <int KIND, int ACT>
 __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_t (&r)[16], int c0, const EpiPos& pos,
-                                               const float* __restrict__ sb) {
+                                               const float* __restrict__ sb, const uint4 (&pfA)[2], const uint4 (&pfB)[2],
+                                               int pfmask) {
     const int n = pos.n0 + c0;
     if (n >= a.Cout) return;  // warp-uniform: padded columns
     float v[16];
@@ -211,7 +229,8 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_
           if (n + j < a.Cout) v[j] += __ldg(rb + j);
       }
     }
-    if (a.preadd != nullptr && pos.valid)
+    if (pfmask & 1) add_prefetched(v, pfA, a.preadd_dtype);
+    else if (a.preadd != nullptr && pos.valid)
       add_residual(v, a.preadd, a.preadd_dtype, pos.pix * a.preadd_cstride + n, full16, a.Cout - n);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -227,9 +246,11 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_
       for (int j = 0; j < 16; ++j)
         if (n + j < a.Cout) v[j] *= __ldg(rs + j);
     }
-    if (a.residual != nullptr && pos.valid)
+    if (pfmask & 2) add_prefetched(v, pfB, a.residual_dtype);
+    else if (a.residual != nullptr && pos.valid)
       add_residual(v, a.residual, a.residual_dtype, pos.pix * a.residual_cstride + n, full16, a.Cout - n);
-    if (a.residual2 != nullptr && pos.valid)
+    if (pfmask & 4) add_prefetched(v, pfA, a.residual2_dtype);
+    else if (a.residual2 != nullptr && pos.valid)
       add_residual(v, a.residual2, a.residual2_dtype, pos.pix * a.residual2_cstride + n, full16, a.Cout - n);
     if (!pos.valid) return;
     if (KIND == 3) {
@@ -293,9 +314,33 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_
 
 // One epilogue warp: accumulator columns [col_begin, col_end) of its 32 TMEM lanes; two 16-column TMEM
 // loads are in flight per wait.
+constexpr int kPfChunks = 4;   // addend prefetch covers up to 4 chunks (64 columns) per warp, i.e. N tiles <= 128
+struct EpiPrefetch {
+  uint4 a[kPfChunks][2], b[kPfChunks][2];
+  int mask;
+};
+
 template <int KIND, int ACT>
 __device__ __forceinline__ void epilogue_cols(const ConvKArgs& a, uint32_t t_addr, int col_begin, int col_end,
-                                              const EpiPos& pos, const float* __restrict__ sb) {
+                                              const EpiPos& pos, const float* __restrict__ sb, const EpiPrefetch& pf) {
+  if (pf.mask != 0) {
+    // <= 4 chunks, all full: chunk index is a compile-time constant so the prefetched vectors stay in registers
+#pragma unroll
+    for (int cp = 0; cp < kPfChunks / 2; ++cp) {
+      const int cc = col_begin + 32 * cp;
+      if (cc < col_end) {  // warp-uniform
+        uint32_t r0[16], r1[16];
+        __syncwarp();
+        tmem_ld16(t_addr + static_cast<uint32_t>(cc), r0);
+        const bool second = cc + 16 < col_end;
+        tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);
+        tmem_ld_wait();
+        epilogue_chunk<KIND, ACT>(a, r0, cc, pos, sb, pf.a[2 * cp], pf.b[2 * cp], pf.mask);
+        if (second) epilogue_chunk<KIND, ACT>(a, r1, cc + 16, pos, sb, pf.a[2 * cp + 1], pf.b[2 * cp + 1], pf.mask);
+      }
+    }
+    return;
+  }
   for (int cc = col_begin; cc < col_end; cc += 32) {
     uint32_t r0[16], r1[16];
     __syncwarp();  // tcgen05.ld is warp-collective: reconverge after divergent stores
@@ -303,8 +348,8 @@ __device__ __forceinline__ void epilogue_cols(const ConvKArgs& a, uint32_t t_add
     const bool second = cc + 16 < col_end;  // warp-uniform
     tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);  // (columns past the tile are allocated, unused)
     tmem_ld_wait();
-    epilogue_chunk<KIND, ACT>(a, r0, cc, pos, sb);
-    if (second) epilogue_chunk<KIND, ACT>(a, r1, cc + 16, pos, sb);
+    epilogue_chunk<KIND, ACT>(a, r0, cc, pos, sb, pf.a[0], pf.b[0], 0);
+    if (second) epilogue_chunk<KIND, ACT>(a, r1, cc + 16, pos, sb, pf.a[0], pf.b[0], 0);
   }
 }
 
@@ -701,6 +746,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // epilogue kind: 0 = fp16 NHWC, 1 = bf16 NHWC, 2 = fp32 NHWC, 3 = fp32 NCHW
     const int kind = (a.out_layout == FLAIR_OUT_NCHW) ? 3 : (a.out_dtype == FLAIR_F32 ? 2 : (a.out_dtype == FLAIR_F16 ? 0 : 1));
     int bias_n = -1, bias_buf = 0;
+    // Addend prefetch: preadd / residual / residual2 (16-bit maps) are loaded BEFORE the wait for the accumulator, so
+    // their L2 latency (~1 us) overlaps the tile's MMAs instead of sitting in the epilogue (per-frame BasicVSR++
+    // launches: 21.4 -> 12.3 us for a 64 -> 64 conv with a pre-activation addend, r02 profile).  Slots: A = preadd, or
+    // residual2 when there is no preadd; B = residual.
+    int pf_mask = 0;
+    {
+      const bool fits = a.pf_ok && (col_end - col_begin) <= 16 * kPfChunks && (a.Cout % 16) == 0;
+      if (fits) {
+        if (a.preadd != nullptr && a.preadd_dtype != FLAIR_F32) pf_mask |= 1;
+        if (a.residual != nullptr && a.residual_dtype != FLAIR_F32) pf_mask |= 2;
+        if (a.residual2 != nullptr && a.residual2_dtype != FLAIR_F32 && !(pf_mask & 1)) pf_mask |= 4;
+      }
+    }
+    EpiPrefetch pf;
+    pf.mask = pf_mask;
     for (int local = 0; local < my_tiles; ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -732,6 +792,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       const float* sb = s_bias[bias_buf];
 
+      if (pf_mask != 0 && pos.valid) {
+        const uint16_t* pa = (pf_mask & 1) ? static_cast<const uint16_t*>(a.preadd) + pos.pix * a.preadd_cstride
+                                           : static_cast<const uint16_t*>(a.residual2) + pos.pix * a.residual2_cstride;
+        const uint16_t* pb = static_cast<const uint16_t*>(a.residual) + pos.pix * a.residual_cstride;
+#pragma unroll
+        for (int ci = 0; ci < kPfChunks; ++ci) {
+          const int c = col_begin + 16 * ci;
+          if (c < col_end) {
+            const int n = pos.n0 + c;
+            if (pf_mask & 5) {
+              pf.a[ci][0] = __ldg(reinterpret_cast<const uint4*>(pa + n));
+              pf.a[ci][1] = __ldg(reinterpret_cast<const uint4*>(pa + n) + 1);
+            }
+            if (pf_mask & 2) {
+              pf.b[ci][0] = __ldg(reinterpret_cast<const uint4*>(pb + n));
+              pf.b[ci][1] = __ldg(reinterpret_cast<const uint4*>(pb + n) + 1);
+            }
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (etid == 0 && local < 4) trace_mark(a.trace, 9 + local);  // accumulator of tile `local` complete
@@ -749,7 +829,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       } else
       switch (kind * 4 + a.act) {
-#define EPI_CASE(K, A) case (K) * 4 + (A): epilogue_cols<K, A>(a, t_addr, col_begin, col_end, pos, sb); break;
+#define EPI_CASE(K, A) case (K) * 4 + (A): epilogue_cols<K, A>(a, t_addr, col_begin, col_end, pos, sb, pf); break;
         EPI_CASE(0, 0) EPI_CASE(0, 1) EPI_CASE(0, 2) EPI_CASE(0, 3)
         EPI_CASE(1, 0) EPI_CASE(1, 1) EPI_CASE(1, 2) EPI_CASE(1, 3)
         EPI_CASE(2, 0) EPI_CASE(2, 1) EPI_CASE(2, 2) EPI_CASE(2, 3)
@@ -930,6 +1010,13 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   a.out_scale = (p->out_scale == 0.0f) ? 1.0f : p->out_scale;
   a.fmt = (p->in_dtype == FLAIR_BF16) ? 1u : 0u;
   a.gn_partial = nullptr; a.gn_groups = 0;
+  {
+    auto vec_ok = [](const void* ptr, int dtype, long long cs) {
+      return ptr == nullptr || dtype == FLAIR_F32 || ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && cs % 8 == 0);
+    };
+    a.pf_ok = vec_ok(p->preadd, p->preadd_dtype, p->preadd_cstride) && vec_ok(p->residual, p->residual_dtype, p->residual_cstride) &&
+              vec_ok(p->residual2, p->residual2_dtype, p->residual2_cstride);
+  }
   a.out2 = static_cast<uint16_t*>(p->out2); a.out2_gs = p->out2_group_channels; a.out2_gstride = p->out2_group_stride;
   if (p->out2 != nullptr)
     FLAIR_REQUIRE(p->out_layout == FLAIR_OUT_NHWC && p->out_dtype != FLAIR_F32 && p->Cout % 16 == 0 &&

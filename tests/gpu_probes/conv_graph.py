@@ -25,4 +25,4 @@ for _ in range(5): g.replay()
 e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / (5 * n)
 gf = 2.0 * T * H * H * cin * cout * 9 / 1e9
-print(f"conv T={T} {H}x{H} {cin}->{cout}: {us:.2f} us per launch in a graph chain  ({gf / us / 1e3:.0f} TFLOP/s)")
+print(f"conv T={T} {H}x{H} {cin}->{cout}: {us:.2f} us per launch in a graph chain  ({gf / us * 1e3:.0f} TFLOP/s)")

@@ -122,6 +122,31 @@ def test_spatial_attention(dev, heads, L):
     assert _rel(y, K.qkv_attention_legacy(qkv, heads)) < 1e-3
 
 
+@pytest.mark.parametrize("heads,hw,dtype,bias", [(4, (16, 16), torch.float16, False), (8, (16, 8), torch.float16, True),
+                                                 (2, (32, 32), torch.float16, False), (4, (16, 16), torch.bfloat16, True)])
+def test_spatial_attention_tensor_core(dev, heads, hw, dtype, bias):
+    """L = H*W a multiple of 128 takes the tcgen05 kernel (QK^T and PV on the tensor cores, fp32 online softmax from
+    TMEM; L = 1024 walks 8 key blocks).  Checked against the fp32 oracle and against the SIMT kernel (FLAIR_ATTN_TC=0
+    is read once per process, so the SIMT result comes from a map whose token count is not a multiple of 128)."""
+    from flair_b200 import ops
+    from oracle import kernels as K
+    H, W = hw
+    g = torch.Generator().manual_seed(heads * H + W)
+    qkv = (torch.randn(1, 2, H, W, heads * 3 * 64, generator=g) * 1.5).to(dtype)
+    rb = torch.randn(2, heads * 64, generator=g) if bias else None
+    y = ops.attn_spatial(qkv.to(dev), heads, rowbias=None if rb is None else rb.to(dev))
+    ref = K.qkv_attention_legacy(qkv.float(), heads)
+    if rb is not None:
+        ref = ref + rb[None, :, None, None, :]
+    tol = 2e-3 if dtype == torch.float16 else 1e-2
+    assert _rel(y, ref) < tol
+    # a strided qkv view (channel stride > 3C) and a wider output go through the same tensor map
+    wide = torch.zeros(1, 2, H, W, heads * 3 * 64 + 64, dtype=dtype, device=dev)
+    wide[..., :heads * 3 * 64] = qkv.to(dev)
+    y2 = ops.attn_spatial(wide[..., :heads * 3 * 64], heads, rowbias=None if rb is None else rb.to(dev))
+    assert torch.equal(y, y2)
+
+
 def test_flow_warp(dev):
     from flair_b200 import ops
     from oracle import kernels as K
