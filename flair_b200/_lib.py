@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libflair_b200.so"
+# FLAIR_B200_LIB: A/B measurements against a library built from another commit (tools/build_ref_lib.sh); never set in
+# production — the default is the in-tree library built by `python -m flair_b200.build`
+import os as _os
+_LIB_PATH = Path(_os.environ.get("FLAIR_B200_LIB") or Path(__file__).resolve().parent / "libflair_b200.so")
 
 BF16, F32, F16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LRELU01, ACT_SILU = 0, 1, 2, 3

@@ -36,7 +36,9 @@ int flair_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("FLAIR_PDL");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;  // measured: no gain inside CUDA graphs -> opt-in
+    // on by default since round 2 (FLAIR_PDL=0 opts out): with the weight prefetch ahead of griddepcontrol.wait the
+    // serial BasicVSR++ chain gains 3-5 % inside CUDA graphs (profiles/r02_summary.md); all GPU tests run with it
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return v;
 }

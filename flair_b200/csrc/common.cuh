@@ -79,8 +79,9 @@ flair_tmap_encode_fn flair_get_tmap_encode();
 // (so the next kernel's CTAs are scheduled, run their prologue and park while this one drains) and
 // griddepcontrol.wait before it touches global memory (which returns once the previous kernel has fully
 // completed and flushed).  A forward is ~5000 short launches: this hides most of the launch latency
-// between them.  Measured on the full forward inside a CUDA graph: no gain (99.7 vs 98.2 ms), so the
-// attribute is opt-in (FLAIR_PDL=1); the griddepcontrol instructions are no-ops without it.
+// between them.  Round 1 measured no gain inside a CUDA graph (every CTA owned its SM, nothing could overlap);
+// since the conv kernel issues its weight loads ahead of griddepcontrol.wait the serial BasicVSR++ chain gains
+// 3-5 %, so the attribute is ON by default (FLAIR_PDL=0 opts out; the instructions are no-ops without it).
 int flair_pdl_enabled();
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -59,7 +59,8 @@ struct ConvKArgs {
   int kblocks, ntaps, stride;
   int trace;   // debug timeline on/off
   int debug;   // FLAIR_CONV_DEBUG bit mask (perf experiments only; results are wrong): 1 = epilogue does nothing,
-               // 2 = epilogue reads TMEM but stores nothing, 4 = producer signals the stages without loading A
+               // 2 = epilogue reads TMEM but stores nothing, 4 = producer signals the stages without loading A,
+               // 8 = the MMA warp does not wait for the accumulator buffer
   int k_last;  // UMMA K=16 steps that hold real channels in the LAST k-block (Cin = 196: 1 of 4)
   int stages;
   // mode 0: one (tap, k-block) per pipeline stage, A tile = 128 output pixels (any kernel / stride / map size).
@@ -91,7 +92,7 @@ struct ConvKArgs {
   uint32_t fmt;
   float* gn_partial;
   int gn_groups;
-  int pf_ok;               // 16-bit addends are 16-byte aligned with channel strides % 8 == 0 (prefetchable as uint4)
+  int fast;                // compact epilogue applies (see epilogue_fast): 1 = no addends, 2 = addends prefetched
   uint16_t* out2;          // optional copy of a 16-bit NHWC output as pair planes [Cout/out2_gs][pixels][2][out2_gs]:
   int out2_gs;             // entry p = (pixel p, pixel p+1), the source layout of flair_deform_conv
   long long out2_gstride;  // elements between group planes
@@ -173,20 +174,6 @@ __device__ __forceinline__ void add_residual(float (&v)[16], const void* base, i
   }
 }
 
-// v[j] += the 16 prefetched 16-bit values of one chunk (two 16-byte vectors)
-__device__ __forceinline__ void add_prefetched(float (&v)[16], const uint4 (&u2)[2], int dtype) {
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const uint32_t uu[4] = {u2[q].x, u2[q].y, u2[q].z, u2[q].w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack16(uu[e], dtype);
-      v[8 * q + 2 * e] += f.x;
-      v[8 * q + 2 * e + 1] += f.y;
-    }
-  }
-}
-
 struct EpiPos {
   int w, h, n0;
   bool valid;
@@ -197,12 +184,9 @@ struct EpiPos {
 // KIND: 0 fp16 NHWC, 1 bf16 NHWC, 2 fp32 NHWC, 3 fp32 NCHW.  ACT: FLAIR_ACT_*.
 // One 16-column chunk of one epilogue warp: bias, per-frame bias, activation, gate, residuals, store.
 // KIND: 0 fp16 NHWC, 1 bf16 NHWC, 2 fp32 NHWC, 3 fp32 NCHW.  ACT: FLAIR_ACT_*.
-// pfmask: addends already in registers (loaded while the MMAs of the tile were still running): bit 0 = preadd in
-// pfA, bit 1 = residual in pfB, bit 2 = residual2 in pfA.
 template <int KIND, int ACT>
 __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_t (&r)[16], int c0, const EpiPos& pos,
-                                               const float* __restrict__ sb, const uint4 (&pfA)[2], const uint4 (&pfB)[2],
-                                               int pfmask) {
+                                               const float* __restrict__ sb) {
     const int n = pos.n0 + c0;
     if (n >= a.Cout) return;  // warp-uniform: padded columns
     float v[16];
@@ -229,8 +213,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_
           if (n + j < a.Cout) v[j] += __ldg(rb + j);
       }
     }
-    if (pfmask & 1) add_prefetched(v, pfA, a.preadd_dtype);
-    else if (a.preadd != nullptr && pos.valid)
+    if (a.preadd != nullptr && pos.valid)
       add_residual(v, a.preadd, a.preadd_dtype, pos.pix * a.preadd_cstride + n, full16, a.Cout - n);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -246,11 +229,9 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_
       for (int j = 0; j < 16; ++j)
         if (n + j < a.Cout) v[j] *= __ldg(rs + j);
     }
-    if (pfmask & 2) add_prefetched(v, pfB, a.residual_dtype);
-    else if (a.residual != nullptr && pos.valid)
+    if (a.residual != nullptr && pos.valid)
       add_residual(v, a.residual, a.residual_dtype, pos.pix * a.residual_cstride + n, full16, a.Cout - n);
-    if (pfmask & 4) add_prefetched(v, pfA, a.residual2_dtype);
-    else if (a.residual2 != nullptr && pos.valid)
+    if (a.residual2 != nullptr && pos.valid)
       add_residual(v, a.residual2, a.residual2_dtype, pos.pix * a.residual2_cstride + n, full16, a.Cout - n);
     if (!pos.valid) return;
     if (KIND == 3) {
@@ -314,33 +295,9 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_
 
 // One epilogue warp: accumulator columns [col_begin, col_end) of its 32 TMEM lanes; two 16-column TMEM
 // loads are in flight per wait.
-constexpr int kPfChunks = 4;   // addend prefetch covers up to 4 chunks (64 columns) per warp, i.e. N tiles <= 128
-struct EpiPrefetch {
-  uint4 a[kPfChunks][2], b[kPfChunks][2];
-  int mask;
-};
-
 template <int KIND, int ACT>
 __device__ __forceinline__ void epilogue_cols(const ConvKArgs& a, uint32_t t_addr, int col_begin, int col_end,
-                                              const EpiPos& pos, const float* __restrict__ sb, const EpiPrefetch& pf) {
-  if (pf.mask != 0) {
-    // <= 4 chunks, all full: chunk index is a compile-time constant so the prefetched vectors stay in registers
-#pragma unroll
-    for (int cp = 0; cp < kPfChunks / 2; ++cp) {
-      const int cc = col_begin + 32 * cp;
-      if (cc < col_end) {  // warp-uniform
-        uint32_t r0[16], r1[16];
-        __syncwarp();
-        tmem_ld16(t_addr + static_cast<uint32_t>(cc), r0);
-        const bool second = cc + 16 < col_end;
-        tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);
-        tmem_ld_wait();
-        epilogue_chunk<KIND, ACT>(a, r0, cc, pos, sb, pf.a[2 * cp], pf.b[2 * cp], pf.mask);
-        if (second) epilogue_chunk<KIND, ACT>(a, r1, cc + 16, pos, sb, pf.a[2 * cp + 1], pf.b[2 * cp + 1], pf.mask);
-      }
-    }
-    return;
-  }
+                                              const EpiPos& pos, const float* __restrict__ sb) {
   for (int cc = col_begin; cc < col_end; cc += 32) {
     uint32_t r0[16], r1[16];
     __syncwarp();  // tcgen05.ld is warp-collective: reconverge after divergent stores
@@ -348,8 +305,130 @@ __device__ __forceinline__ void epilogue_cols(const ConvKArgs& a, uint32_t t_add
     const bool second = cc + 16 < col_end;  // warp-uniform
     tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);  // (columns past the tile are allocated, unused)
     tmem_ld_wait();
-    epilogue_chunk<KIND, ACT>(a, r0, cc, pos, sb, pf.a[0], pf.b[0], 0);
-    if (second) epilogue_chunk<KIND, ACT>(a, r1, cc + 16, pos, sb, pf.a[0], pf.b[0], 0);
+    epilogue_chunk<KIND, ACT>(a, r0, cc, pos, sb);
+    if (second) epilogue_chunk<KIND, ACT>(a, r1, cc + 16, pos, sb);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Compact epilogue for the common case: 16-bit NHWC output, Cout % 16 == 0, 32-byte aligned rows, no per-frame
+// bias / gate.  The generic path above is ~2700 instructions per (output kind, activation) instance with all its
+// partial-chunk and layout branches; on N = 64 tiles (every 64-channel conv of the 256 x 256 maps) the tensor pipe
+// needs only ~1.5 us per tile and that epilogue did not fit behind it (profiles/r02_summary.md: 61 us per launch,
+// 50 us with the epilogue's arithmetic and stores removed).  Here everything that varies per launch is a warp-uniform
+// branch around a 16-element loop, and the 16-bit addends (preadd / residual / residual2) are loaded BEFORE the wait
+// for the accumulator, so their L2 latency overlaps the tile's MMAs.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPfChunks = 4;   // addend prefetch covers up to 4 chunks (64 columns) per warp, i.e. N tiles <= 128
+struct EpiPrefetch {
+  uint4 a[kPfChunks][2], b[kPfChunks][2];   // slot A = preadd, or residual2 when there is no preadd; slot B = residual
+};
+
+__device__ __forceinline__ void add16(float (&v)[16], const uint4 (&u2)[2], bool f16) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint32_t uu[4] = {u2[q].x, u2[q].y, u2[q].z, u2[q].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f;
+      if (f16) f = __half22float2(*reinterpret_cast<const __half2*>(&uu[e]));
+      else f = unpack_bf16x2(uu[e]);
+      v[8 * q + 2 * e] += f.x;
+      v[8 * q + 2 * e + 1] += f.y;
+    }
+  }
+}
+
+// one 16-column chunk: bias, [preadd], activation, [scale], [residuals], pack, one 32-byte store (+ pair planes)
+// mask: bit 0 preadd (slot A), bit 1 residual (slot B), bit 2 residual2 (slot A)
+__device__ __forceinline__ void fast_chunk(const ConvKArgs& a, const uint32_t (&r)[16], int c0, int n, long long pix,
+                                           bool valid, const float* __restrict__ sb, const uint4 (&pa)[2],
+                                           const uint4 (&pb)[2], int mask, bool f16) {
+  float v[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 bq = *reinterpret_cast<const float4*>(sb + c0 + 4 * q);
+    v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bq.x;
+    v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq.y;
+    v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq.z;
+    v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq.w;
+  }
+  if (mask & 1) add16(v, pa, f16);
+  if (a.act == FLAIR_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (a.act == FLAIR_ACT_LRELU01) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);   // == v > 0 ? v : 0.1 v
+  } else if (a.act == FLAIR_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+  }
+  if (a.out_scale != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= a.out_scale;
+  }
+  if (mask & 2) add16(v, pb, f16);
+  if (mask & 4) add16(v, pa, f16);
+  if (!valid) return;
+  uint32_t u[8];
+  if (f16) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      u[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  }
+  uint16_t* op = static_cast<uint16_t*>(a.out) + pix * a.out_cstride + n;
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
+               "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+               : "memory");
+  if (a.out2 != nullptr) {  // pair planes for the deformable gather: slot 0 of entry pix, slot 1 of entry pix-1
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int ch = n + 8 * q;
+      uint16_t* e = a.out2 + (ch / a.out2_gs) * a.out2_gstride + pix * (2 * a.out2_gs) + (ch % a.out2_gs);
+      const uint4 uq = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+      *reinterpret_cast<uint4*>(e) = uq;
+      if (pix > 0) *reinterpret_cast<uint4*>(e - a.out2_gs) = uq;
+    }
+  }
+}
+
+// PF: addends are in registers (<= 4 chunks per warp, chunk index compile-time)
+template <bool PF>
+__device__ __forceinline__ void epilogue_fast(const ConvKArgs& a, uint32_t t_addr, int col_begin, int col_end, int n0,
+                                              long long pix, bool valid, const float* __restrict__ sb,
+                                              const EpiPrefetch& pf, int mask, bool f16) {
+  if (PF) {
+#pragma unroll
+    for (int cp = 0; cp < kPfChunks / 2; ++cp) {
+      const int cc = col_begin + 32 * cp;
+      if (cc < col_end) {  // warp-uniform
+        uint32_t r0[16], r1[16];
+        __syncwarp();
+        tmem_ld16(t_addr + static_cast<uint32_t>(cc), r0);
+        tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);
+        tmem_ld_wait();
+        fast_chunk(a, r0, cc, n0 + cc, pix, valid, sb, pf.a[2 * cp], pf.b[2 * cp], mask, f16);
+        if (cc + 16 < col_end) fast_chunk(a, r1, cc + 16, n0 + cc + 16, pix, valid, sb, pf.a[2 * cp + 1], pf.b[2 * cp + 1], mask, f16);
+      }
+    }
+  } else {
+    const uint4 none[2] = {};
+#pragma unroll 1
+    for (int cc = col_begin; cc < col_end; cc += 32) {
+      uint32_t r0[16], r1[16];
+      __syncwarp();
+      tmem_ld16(t_addr + static_cast<uint32_t>(cc), r0);
+      tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);
+      tmem_ld_wait();
+      fast_chunk(a, r0, cc, n0 + cc, pix, valid, sb, none, none, 0, f16);
+      if (cc + 16 < col_end) fast_chunk(a, r1, cc + 16, n0 + cc + 16, pix, valid, sb, none, none, 0, f16);
+    }
   }
 }
 
@@ -572,7 +651,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int local = 0; local < my_tiles; ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      if (!(a.debug & 8)) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * a.acc_cols);
       if (lane == 0 && local < 4) trace_mark(a.trace, 5 + local);  // MMA of tile `local` may start (TMEM buffer free)
@@ -746,21 +825,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // epilogue kind: 0 = fp16 NHWC, 1 = bf16 NHWC, 2 = fp32 NHWC, 3 = fp32 NCHW
     const int kind = (a.out_layout == FLAIR_OUT_NCHW) ? 3 : (a.out_dtype == FLAIR_F32 ? 2 : (a.out_dtype == FLAIR_F16 ? 0 : 1));
     int bias_n = -1, bias_buf = 0;
-    // Addend prefetch: preadd / residual / residual2 (16-bit maps) are loaded BEFORE the wait for the accumulator, so
-    // their L2 latency (~1 us) overlaps the tile's MMAs instead of sitting in the epilogue (per-frame BasicVSR++
-    // launches: 21.4 -> 12.3 us for a 64 -> 64 conv with a pre-activation addend, r02 profile).  Slots: A = preadd, or
-    // residual2 when there is no preadd; B = residual.
-    int pf_mask = 0;
-    {
-      const bool fits = a.pf_ok && (col_end - col_begin) <= 16 * kPfChunks && (a.Cout % 16) == 0;
-      if (fits) {
-        if (a.preadd != nullptr && a.preadd_dtype != FLAIR_F32) pf_mask |= 1;
-        if (a.residual != nullptr && a.residual_dtype != FLAIR_F32) pf_mask |= 2;
-        if (a.residual2 != nullptr && a.residual2_dtype != FLAIR_F32 && !(pf_mask & 1)) pf_mask |= 4;
-      }
-    }
+    const int pf_mask = (a.fast == 2) ? ((a.preadd ? 1 : 0) | (a.residual ? 2 : 0) | ((a.residual2 && !a.preadd) ? 4 : 0)) : 0;
     EpiPrefetch pf;
-    pf.mask = pf_mask;
     for (int local = 0; local < my_tiles; ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -792,7 +858,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       const float* sb = s_bias[bias_buf];
 
-      if (pf_mask != 0 && pos.valid) {
+      if (a.fast == 2 && pos.valid) {   // addends of this warp's chunks -> registers, before the accumulator wait
         const uint16_t* pa = (pf_mask & 1) ? static_cast<const uint16_t*>(a.preadd) + pos.pix * a.preadd_cstride
                                            : static_cast<const uint16_t*>(a.residual2) + pos.pix * a.residual2_cstride;
         const uint16_t* pb = static_cast<const uint16_t*>(a.residual) + pos.pix * a.residual_cstride;
@@ -827,9 +893,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (r0[0] == 0x7fc12345u && pos.valid) static_cast<uint16_t*>(a.out)[0] = 0;  // keep the load alive
           }
         }
+      } else if (a.fast == 2) {
+        epilogue_fast<true>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, pf_mask, a.out_dtype == FLAIR_F16);
+      } else if (a.fast == 1) {
+        epilogue_fast<false>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, 0, a.out_dtype == FLAIR_F16);
       } else
       switch (kind * 4 + a.act) {
-#define EPI_CASE(K, A) case (K) * 4 + (A): epilogue_cols<K, A>(a, t_addr, col_begin, col_end, pos, sb, pf); break;
+#define EPI_CASE(K, A) case (K) * 4 + (A): epilogue_cols<K, A>(a, t_addr, col_begin, col_end, pos, sb); break;
         EPI_CASE(0, 0) EPI_CASE(0, 1) EPI_CASE(0, 2) EPI_CASE(0, 3)
         EPI_CASE(1, 0) EPI_CASE(1, 1) EPI_CASE(1, 2) EPI_CASE(1, 3)
         EPI_CASE(2, 0) EPI_CASE(2, 1) EPI_CASE(2, 2) EPI_CASE(2, 3)
@@ -1011,11 +1081,24 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   a.fmt = (p->in_dtype == FLAIR_BF16) ? 1u : 0u;
   a.gn_partial = nullptr; a.gn_groups = 0;
   {
+    // compact epilogue: 16-bit NHWC rows of whole 32-byte chunks, no per-frame bias / gate; addends (if any) 16-bit,
+    // vector-aligned, at most one of preadd / residual2 next to residual, and <= 4 chunks per epilogue warp
     auto vec_ok = [](const void* ptr, int dtype, long long cs) {
-      return ptr == nullptr || dtype == FLAIR_F32 || ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && cs % 8 == 0);
+      return ptr == nullptr || (dtype != FLAIR_F32 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && cs % 8 == 0);
     };
-    a.pf_ok = vec_ok(p->preadd, p->preadd_dtype, p->preadd_cstride) && vec_ok(p->residual, p->residual_dtype, p->residual_cstride) &&
-              vec_ok(p->residual2, p->residual2_dtype, p->residual2_cstride);
+    const bool plain = p->out_layout == FLAIR_OUT_NHWC && p->out_dtype != FLAIR_F32 && p->Cout % 16 == 0 &&
+                       (reinterpret_cast<uintptr_t>(p->out) & 31) == 0 && p->out_cstride % 16 == 0 &&
+                       p->rowbias == nullptr && p->rowscale == nullptr;
+    const bool any_add = p->preadd || p->residual || p->residual2;
+    const bool add_ok = vec_ok(p->preadd, p->preadd_dtype, p->preadd_cstride) &&
+                        vec_ok(p->residual, p->residual_dtype, p->residual_cstride) &&
+                        vec_ok(p->residual2, p->residual2_dtype, p->residual2_cstride) &&
+                        !(p->preadd && p->residual2) && n_tile <= 32 * kPfChunks;
+    const bool same_dt = (!p->preadd || p->preadd_dtype == p->out_dtype) && (!p->residual || p->residual_dtype == p->out_dtype) &&
+                         (!p->residual2 || p->residual2_dtype == p->out_dtype);
+    static int fast_env = -1;
+    if (fast_env < 0) { const char* e = getenv("FLAIR_CONV_FAST_EPI"); fast_env = e ? atoi(e) : 1; }
+    a.fast = (!plain || !fast_env) ? 0 : (!any_add ? 1 : ((add_ok && same_dt) ? 2 : 0));
   }
   a.out2 = static_cast<uint16_t*>(p->out2); a.out2_gs = p->out2_group_channels; a.out2_gstride = p->out2_group_stride;
   if (p->out2 != nullptr)
