@@ -602,7 +602,7 @@ def fwd_sweep(model, dev, pk, batches):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        tf = GF_IMAGE["blur"] * n / ms / 1e3
+        tf = GF_IMAGE["blur"] * n / ms   # GF per ms == TFLOP/s
         rows.append({"frames": n, "ms": ms, "tflops": tf, "frac_of_peak": tf / pk["tflops"]})
     return rows
 

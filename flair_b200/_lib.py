@@ -32,6 +32,7 @@ class ConvParams(C.Structure):
         ("out_scale", C.c_float), ("gn_partial", C.c_void_p), ("gn_groups", C.c_int),
         ("out2", C.c_void_p), ("out2_group_channels", C.c_int), ("out2_group_stride", C.c_longlong),
         ("preadd", C.c_void_p), ("preadd_dtype", C.c_int), ("preadd_cstride", C.c_int),
+        ("out2_neighbor", C.c_int),
     ]
 
 

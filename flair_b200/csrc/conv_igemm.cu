@@ -96,6 +96,8 @@ struct ConvKArgs {
   uint16_t* out2;          // optional copy of a 16-bit NHWC output as pair planes [Cout/out2_gs][pixels][2][out2_gs]:
   int out2_gs;             // entry p = (pixel p, pixel p+1), the source layout of flair_deform_conv
   long long out2_gstride;  // elements between group planes
+  long long out2_back;     // elements from slot 0 of entry pix back to slot 1 of entry pix - neighbor
+  int out2_nb;             // neighbor distance in pixels: 1 (x, x+1 pairs) or W (y, y+1 pairs)
 };
 
 // Debug timeline: in a library built with -DFLAIR_CONV_TRACE_BUILD (FLAIR_BUILD_TRACE=1 python -m flair_b200.build)
@@ -282,7 +284,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKArgs& a, const uint32_
             const int ch = n + 8 * q;
             uint16_t* e = a.out2 + (ch / a.out2_gs) * a.out2_gstride + pos.pix * (2 * a.out2_gs) + (ch % a.out2_gs);
             *reinterpret_cast<uint4*>(e) = u;
-            if (pos.pix > 0) *reinterpret_cast<uint4*>(e - a.out2_gs) = u;
+            if (pos.pix >= a.out2_nb) *reinterpret_cast<uint4*>(e - a.out2_back) = u;
           }
         }
       } else {
@@ -393,7 +395,7 @@ __device__ __forceinline__ void fast_chunk(const ConvKArgs& a, const uint32_t (&
       uint16_t* e = a.out2 + (ch / a.out2_gs) * a.out2_gstride + pix * (2 * a.out2_gs) + (ch % a.out2_gs);
       const uint4 uq = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
       *reinterpret_cast<uint4*>(e) = uq;
-      if (pix > 0) *reinterpret_cast<uint4*>(e - a.out2_gs) = uq;
+      if (pix >= a.out2_nb) *reinterpret_cast<uint4*>(e - a.out2_back) = uq;
     }
   }
 }
@@ -1101,6 +1103,8 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
     a.fast = (!plain || !fast_env) ? 0 : (!any_add ? 1 : ((add_ok && same_dt) ? 2 : 0));
   }
   a.out2 = static_cast<uint16_t*>(p->out2); a.out2_gs = p->out2_group_channels; a.out2_gstride = p->out2_group_stride;
+  a.out2_nb = p->out2_neighbor > 0 ? p->out2_neighbor : 1;
+  a.out2_back = static_cast<long long>(a.out2_nb) * 2 * a.out2_gs - a.out2_gs;
   if (p->out2 != nullptr)
     FLAIR_REQUIRE(p->out_layout == FLAIR_OUT_NHWC && p->out_dtype != FLAIR_F32 && p->Cout % 16 == 0 &&
                       (p->out2_group_channels == 8 || p->out2_group_channels == 16) && p->out2_group_stride % 8 == 0 &&

@@ -70,6 +70,7 @@ struct DeformArgs {
   uint32_t b_bytes, stage_bytes;
   float mrm;
   uint32_t fmt;
+  int coop;  // lane-pair gather (see the producer loop): 1 = on
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -192,7 +193,7 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
   constexpr int tmem_cols = 2 * n_tile;     // 128 or 256
   // producer warps = 4 row quarters x 4 group quads.  C = 64: a k-block (one tap, one source) holds 8 groups ->
   // filled by 2 quads x 4 quarters; C = 128: 4 groups per k-block -> 1 quad x 4 quarters.
-  constexpr int prod_arrivals = (VPG == 1) ? 8 : 4;
+  constexpr int prod_arrivals = kProdWarps;   // all 16 gather warps fill every k-block
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmB);
@@ -239,18 +240,20 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
         const int tile = blockIdx.x + i * gridDim.x;
         int tn, th0, tw0;
         tile_origin(a, tile, tn, th0, tw0);
-        for (int tap = 0; tap < 9; ++tap) {
+        // channel-block-major K order: all nine taps of one 64-channel block of cat(xa, xb), then the next block.
+        // The gather of a block touches 8 (C = 64) / 4 (C = 128) source planes only, so its working set (~100 KB per
+        // 16 x 8 tile) stays in L1 across the nine taps; in tap-major order every tap swept all 16 planes and the L1
+        // hit rate was 26 % (the kernel then ran at the L2's random-sector throughput, ~4.5 TB/s, at both shapes).
+        for (int it = 0; it < 9 * a.kpt; ++it) {
+          const int tap = it % 9;
           mbar_wait(&om_empty[os], ophase ^ 1);
           mbar_expect_tx(&om_full[os], kOmBytes);
           tma_load_4d(smem_om + os * kOmBytes, &tmOM, &om_full[os], tap * 48, tw0, th0, tn);
           if (++os == kOmStages) { os = 0; ophase ^= 1; }
-          for (int j = 0; j < a.kpt; ++j) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], a.b_bytes);
-            tma_load_2d(smem + static_cast<size_t>(stage) * a.stage_bytes + kABytes, &tmB, &full_bar[stage],
-                        (tap * a.kpt + j) * kBlockK, 0);
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
-          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], a.b_bytes);
+          tma_load_2d(smem + static_cast<size_t>(stage) * a.stage_bytes + kABytes, &tmB, &full_bar[stage], it * kBlockK, 0);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -331,34 +334,29 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
     }
   } else {
     // ===================== gather producers (warps 6..21) =====================
-    // Warp (rq, quad) owns tile rows rq*32..+31 (lane = pixel) x deform groups quad*4..+3: 4 samples per lane per
-    // tap.  Sources are "pair planes" [group][pixel][2][C/8]: entry p holds pixels p and p+1 of the row-major map,
-    // so the two x-corners of a bilinear sample are ONE aligned 32-byte (C = 64) / 64-byte (C = 128) load and a
-    // sample costs two L1 tag look-ups (one per row) instead of four.  The kernel is bound by L1 wavefronts
-    // (ncu: l1tex 82 % busy, L2 19 %, once the carve-out leaves L1 room for the ~36x re-read of every source
-    // pixel), so look-ups per sample are what matters; a 4-lanes-per-sample variant with shuffles had the same
-    // look-up count but 3x the instructions and as many shuffle wavefronts again.
+    // K is walked channel-block-major (see the TMA warp): k-block it = (kbq, tap), kbq = 64-channel block of
+    // cat(xa, xb).  All 16 warps fill the SAME k-block: warp (rq, sub) owns tile rows rq*32..+31 and
+    //   C = 64 : groups kbq*8 + sub*2 + {0, 1}  (two samples per lane, 16-byte chunks sub*2 + {0, 1} of the operand row)
+    //   C = 128: group  kbq*4 + sub             (one sample of 16 channels, chunks sub*2 + {0, 1})
+    // Sources are "pair planes" [group][pixel][2][C/8]: entry p holds pixels p and p+1 of the row-major map, so the
+    // two x-corners of a bilinear sample are ONE aligned 32-byte (C = 64) / 64-byte (C = 128) read.
+    //   C = 64 : lane = pixel, 2 samples x 2 rows = 4 LDG.256 in flight per lane.
+    //   C = 128: lane pairs — lanes 2k / 2k+1 fetch slot 0 / slot 1 of the same 64-byte entry in one instruction (one
+    //            L1 line access instead of two), blend their column over the two rows and exchange half of the 16
+    //            channels, so each lane stores 8 finished channels; the sample geometry is computed once by the lane
+    //            that owns the pixel and handed to the pair with 4 shuffles.
     const int pw = warp - (2 + kEpiWarps);
     const int rq = pw & 3;        // row quarter of the tile
-    const int quad = pw >> 2;     // deform groups quad*4 .. quad*4+3
-    const int half = quad >> 1;   // 0: groups 0..7 sample xa (flow1), 1: groups 8..15 sample xb (flow2)
+    const int sub = pw >> 2;      // 0..3
     const int row = rq * 32 + lane;
-    const uint16_t* src = a.src[half] + static_cast<long long>((quad & 1) * 4) * a.src_gstride[half];
-    const long long gstride = a.src_gstride[half];
-    const int nstride = static_cast<int>(a.src_nstride[half]);  // (< 2^31, host-checked)
-    const int pstride = a.src_pstride[half];                    // elements per pair entry = 2 * C/8
-    const int wps = a.W * pstride;
-    const float* fl = half ? a.flow2 : a.flow1;
     const int H = a.H, W = a.W;
     const float Hf = static_cast<float>(H), Wf = static_cast<float>(W);
-    // k-block of this warp inside a tap and the first 16-byte chunk it writes in each operand row
-    const int kb_in_tap = (VPG == 1) ? half : quad;
-    const int chunk0 = (VPG == 1) ? (quad & 1) * 4 : 0;
-    const uint32_t om_row = smem_u32(smem_om) + row * 96 + quad * 24;
-    const uint32_t a_row = smem_u32(smem) + row * 128;
     const int sw = row & 7;
+    const uint32_t a_row = smem_u32(smem) + row * 128;
     int os = 0;
     uint32_t ophase = 0;
+    int stage = 0;
+    uint32_t phase = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
       int n, th0, tw0;
@@ -366,77 +364,168 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
       const int h = th0 + (row >> 4), w = tw0 + (row & 15);
       const bool valid = h < H && w < W;
       const int off = valid ? h * W + w : 0;
-      const float fy = valid ? __ldg(fl + (static_cast<long long>(n) * 2 + 1) * hw + off) : 0.f;
-      const float fx = valid ? __ldg(fl + (static_cast<long long>(n) * 2 + 0) * hw + off) : 0.f;
-      const uint16_t* img = src + n * nstride;
-      const int kb_base = i * kb_per_tile + kb_in_tap;
+      float fyx[2][2];   // [source half][y, x] flow of this pixel
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const float* fl = hf ? a.flow2 : a.flow1;
+        fyx[hf][0] = valid ? __ldg(fl + (static_cast<long long>(n) * 2 + 1) * hw + off) : 0.f;
+        fyx[hf][1] = valid ? __ldg(fl + (static_cast<long long>(n) * 2 + 0) * hw + off) : 0.f;
+      }
 #pragma unroll 1
-      for (int tap = 0; tap < 9; ++tap) {
-        // ---- this tap's (dy x4 | dx x4 | mask x4) of the warp's quad
+      for (int it = 0; it < kb_per_tile; ++it) {
+        const int kbq = it / 9, tap = it - kbq * 9;
+        // group(s) of this warp in this k-block, their source half / plane, and their offset quad
+        const int g0 = (VPG == 1) ? kbq * 8 + sub * 2 : kbq * 4 + sub;
+        const int half = g0 >> 3;                 // 0: xa (flow1), 1: xb (flow2)
+        const int plane0 = g0 & 7;
+        const int quad = g0 >> 2, gq = g0 & 3;    // offset quad and index inside it
+        const uint16_t* img = a.src[half] + static_cast<long long>(plane0) * a.src_gstride[half] + n * static_cast<int>(a.src_nstride[half]);
+        const long long gstride = a.src_gstride[half];
+        const int pstride = a.src_pstride[half];
+        const int wps = W * pstride;
+        const float fy = half ? fyx[1][0] : fyx[0][0], fx = half ? fyx[1][1] : fyx[0][1];
+        // ---- this tap's (dy x4 | dx x4 | mask x4) of the quad
         mbar_wait(&om_full[os], ophase);
-        const uint2 rdy = lds64(om_row + os * kOmBytes), rdx = lds64(om_row + os * kOmBytes + 8), rmk = lds64(om_row + os * kOmBytes + 16);
-        // NOTE: the slot is released at the END of the tap.  Releasing it here, right after the loads were ISSUED,
-        // lost data: nothing made the mbarrier arrive wait for the LDS results, and with 22 warps polling barriers
-        // the loads could still be queued when the TMA refill of the slot landed (measured: a whole warp then
-        // sampled with the offsets of a later tap).  At the end of the tap the values have been consumed.
+        const uint32_t om_row = smem_u32(smem_om) + os * kOmBytes + row * 96 + quad * 24;
+        const uint2 rdy = lds64(om_row), rdx = lds64(om_row + 8), rmk = lds64(om_row + 16);
+        // NOTE: the slot is released at the END of the k-block, after the values were consumed (an arrive issued right
+        // after the ld.shared does not wait for the loads).
         const int tdy = tap / 3 - 1, tdx = tap - (tap / 3) * 3 - 1;
         const float by = static_cast<float>(h + tdy) + fy;
         const float bx = static_cast<float>(w + tdx) + fx;
-        const int kb = kb_base + tap * a.kpt;
-        const int stage = kb % a.stages;
-        const uint32_t phase = static_cast<uint32_t>(kb / a.stages) & 1u;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        const uint32_t arow = a_row + static_cast<uint32_t>(stage) * a.stage_bytes;
-        constexpr int SB = (VPG == 1) ? 2 : 1;  // samples whose loads are in flight together (4 x 32 bytes each way)
+        const uint32_t stage_base = smem_u32(smem) + static_cast<uint32_t>(stage) * a.stage_bytes;
+        // sample geometry of group index gi (inside the quad) at this lane's pixel
+        auto geometry = [&](int gi, int& o0, int& o1, float (&wgt)[4]) {
+          const float2 pdy = unpack2<false>(gi < 2 ? rdy.x : rdy.y), pdx = unpack2<false>(gi < 2 ? rdx.x : rdx.y),
+                       pmk = unpack2<false>(gi < 2 ? rmk.x : rmk.y);
+          const float sy = by + a.mrm * tanh_fast((gi & 1) ? pdy.y : pdy.x);
+          const float sx = bx + a.mrm * tanh_fast((gi & 1) ? pdx.y : pdx.x);
+          float mk = __fdividef(1.0f, 1.0f + __expf(-((gi & 1) ? pmk.y : pmk.x)));
+          // torchvision bilinear_interpolate: zero outside (-1, H) x (-1, W); corners outside the map contribute 0
+          if (!(valid && sy > -1.f && sy < Hf && sx > -1.f && sx < Wf)) mk = 0.f;
+          const float fy0 = floorf(sy), fx0 = floorf(sx);
+          const float ay = sy - fy0, ax = sx - fx0;
+          const int y0 = static_cast<int>(fmaxf(fminf(fy0, Hf), -2.f)), x0 = static_cast<int>(fmaxf(fminf(fx0, Wf), -2.f));
+          const float wy0 = (y0 >= 0) ? (1.f - ay) * mk : 0.f, wy1 = (y0 + 1 <= H - 1) ? ay * mk : 0.f;
+          // pair entry xs holds pixels (xs, xs+1).  x0 = -1: the right corner (pixel 0) is slot 0 of entry 0.
+          const float wxr = (x0 + 1 <= W - 1) ? ax : 0.f;
+          const float wxa = (x0 >= 0) ? 1.f - ax : wxr, wxb = (x0 >= 0) ? wxr : 0.f;
+          wgt[0] = wy0 * wxa; wgt[1] = wy0 * wxb; wgt[2] = wy1 * wxa; wgt[3] = wy1 * wxb;
+          // clamped coordinates: a corner with zero weight may read any valid entry
+          const int y0c = min(max(y0, 0), H - 1), y1c = min(max(y0 + 1, 0), H - 1), xs = min(max(x0, 0), W - 1);
+          o0 = y0c * wps + xs * pstride;
+          o1 = y1c * wps + xs * pstride;
+        };
+        if (VPG == 1) {
+          // ---- C = 64: two samples (groups g0, g0 + 1) per lane, 4 x LDG.256 in flight.
+          // (A lane-pair variant over VERTICAL pair planes — the two corner columns of a sample fetched by two lanes in
+          // one instruction, 1.47 instead of 2 global data-pipe wavefronts per sample — was measured in round 2: the
+          // six shuffles per 16 samples it needs go through the same l1tex data pipe and gave the wavefronts back
+          // (170.8K -> 166.7K per SM, 101 -> 112 us in situ), see profiles/r02_summary.md.)
+          uint32_t v[2][2][2][4];  // [sample][row][slot][words]
+          float wgt[2][4];
 #pragma unroll
-        for (int g0 = 0; g0 < 4; g0 += SB) {
-          uint32_t v[SB][2][2 * VPG][4];  // [sample][row][16-byte vector: slot0 vecs, slot1 vecs][words]
-          float wgt[SB][4];               // row0*slot0, row0*slot1, row1*slot0, row1*slot1
-#pragma unroll
-          for (int sgi = 0; sgi < SB; ++sgi) {
-            const int gi = g0 + sgi;
-            // the offset map is always fp16 (bf16 would quantise a 10-pixel offset to 0.04 px)
-            const float2 pdy = unpack2<false>(gi < 2 ? rdy.x : rdy.y), pdx = unpack2<false>(gi < 2 ? rdx.x : rdx.y),
-                         pmk = unpack2<false>(gi < 2 ? rmk.x : rmk.y);
-            const float sy = by + a.mrm * tanh_fast((gi & 1) ? pdy.y : pdy.x);
-            const float sx = bx + a.mrm * tanh_fast((gi & 1) ? pdx.y : pdx.x);
-            float mk = __fdividef(1.0f, 1.0f + __expf(-((gi & 1) ? pmk.y : pmk.x)));
-            // torchvision bilinear_interpolate: zero outside (-1, H) x (-1, W); corners outside the map contribute 0
-            if (!(valid && sy > -1.f && sy < Hf && sx > -1.f && sx < Wf)) mk = 0.f;
-            const float fy0 = floorf(sy), fx0 = floorf(sx);
-            const float ay = sy - fy0, ax = sx - fx0;
-            const int y0 = static_cast<int>(fmaxf(fminf(fy0, Hf), -2.f)), x0 = static_cast<int>(fmaxf(fminf(fx0, Wf), -2.f));
-            const float wy0 = (y0 >= 0) ? (1.f - ay) * mk : 0.f, wy1 = (y0 + 1 <= H - 1) ? ay * mk : 0.f;
-            // pair entry xs holds pixels (xs, xs+1).  x0 = -1: the right corner (pixel 0) is slot 0 of entry 0.
-            const float wxr = (x0 + 1 <= W - 1) ? ax : 0.f;
-            const float wxa = (x0 >= 0) ? 1.f - ax : wxr, wxb = (x0 >= 0) ? wxr : 0.f;
-            wgt[sgi][0] = wy0 * wxa; wgt[sgi][1] = wy0 * wxb; wgt[sgi][2] = wy1 * wxa; wgt[sgi][3] = wy1 * wxb;
-            // clamped coordinates: a corner with zero weight may read any valid entry
-            const int y0c = min(max(y0, 0), H - 1), y1c = min(max(y0 + 1, 0), H - 1), xs = min(max(x0, 0), W - 1);
-            const uint16_t* gbase = img + gi * gstride + xs * pstride;
-            const uint16_t* r0p = gbase + y0c * wps;
-            const uint16_t* r1p = gbase + y1c * wps;
-#pragma unroll
-            for (int q = 0; q < VPG; ++q) {  // 32 bytes per load: C = 64 -> (slot0, slot1); C = 128 -> q = slot
-              ldg256(r0p + q * 16, v[sgi][0][2 * q], v[sgi][0][2 * q + 1]);
-              ldg256(r1p + q * 16, v[sgi][1][2 * q], v[sgi][1][2 * q + 1]);
-            }
+          for (int sgi = 0; sgi < 2; ++sgi) {
+            int o0, o1;
+            geometry(gq + sgi, o0, o1, wgt[sgi]);
+            const uint16_t* gb = img + sgi * gstride;
+            ldg256(gb + o0, v[sgi][0][0], v[sgi][0][1]);
+            ldg256(gb + o1, v[sgi][1][0], v[sgi][1][1]);
           }
 #pragma unroll
-          for (int sgi = 0; sgi < SB; ++sgi) {
-            const int gi = g0 + sgi;
+          for (int sgi = 0; sgi < 2; ++sgi) {
+            uint4 c4[4];
 #pragma unroll
-            for (int vi = 0; vi < VPG; ++vi) {
-              // corner vectors of output vector vi: slot s of row r = v[sgi][r][s * VPG + vi]
-              uint4 c4[4];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const uint32_t* pv = v[sgi][c >> 1][(c & 1) * VPG + vi];
-                c4[c] = make_uint4(pv[0], pv[1], pv[2], pv[3]);
-              }
-              const uint4 o = blend4<BF16>(c4, wgt[sgi]);
-              sts128(arow + (((chunk0 + gi * VPG + vi) ^ sw) << 4), o.x, o.y, o.z, o.w);
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t* pv = v[sgi][c >> 1][c & 1];
+              c4[c] = make_uint4(pv[0], pv[1], pv[2], pv[3]);
             }
+            const uint4 o = blend4<BF16>(c4, wgt[sgi]);
+            sts128(stage_base + row * 128 + (((sub * 2 + sgi) ^ sw) << 4), o.x, o.y, o.z, o.w);
+          }
+        } else if (!a.coop) {
+          // ---- C = 128, one lane per sample: 4 x LDG.256 (2 rows x 2 slots of 16 channels)
+          uint32_t v[2][4][4];  // [row][16-byte vector: slot0 lo, slot0 hi, slot1 lo, slot1 hi][words]
+          float wgt[4];
+          int o0, o1;
+          geometry(gq, o0, o1, wgt);
+          ldg256(img + o0, v[0][0], v[0][1]);
+          ldg256(img + o0 + 16, v[0][2], v[0][3]);
+          ldg256(img + o1, v[1][0], v[1][1]);
+          ldg256(img + o1 + 16, v[1][2], v[1][3]);
+#pragma unroll
+          for (int vi = 0; vi < 2; ++vi) {
+            uint4 c4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t* pv = v[c >> 1][(c & 1) * 2 + vi];
+              c4[c] = make_uint4(pv[0], pv[1], pv[2], pv[3]);
+            }
+            const uint4 o = blend4<BF16>(c4, wgt);
+            sts128(stage_base + row * 128 + (((sub * 2 + vi) ^ sw) << 4), o.x, o.y, o.z, o.w);
+          }
+        } else {
+          // ---- C = 128, lane pairs
+          const int s_slot = lane & 1;
+          float wgt[4];
+          int off0, off1;
+          geometry(gq, off0, off1, wgt);
+          // weights as (slot 0, slot 1) half pairs per row
+          const uint32_t wrow0 = pack2<false>(wgt[0], wgt[1]), wrow1 = pack2<false>(wgt[2], wgt[3]);
+          const uint16_t* gplane = img + s_slot * 16;
+          uint32_t v[2][2][8];   // [pixel half][row][8 words = 16 channels]
+          uint32_t wsel[2][2];   // [pixel half][row]: this lane's weight, broadcast to both halves
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {
+            const int srcl = 16 * ph + (lane >> 1);
+            const int o0 = __shfl_sync(0xffffffffu, off0, srcl), o1 = __shfl_sync(0xffffffffu, off1, srcl);
+            const uint32_t w0 = __shfl_sync(0xffffffffu, wrow0, srcl), w1 = __shfl_sync(0xffffffffu, wrow1, srcl);
+            wsel[ph][0] = __byte_perm(w0, 0, s_slot ? 0x3232 : 0x1010);
+            wsel[ph][1] = __byte_perm(w1, 0, s_slot ? 0x3232 : 0x1010);
+            uint32_t (&a0)[8] = v[ph][0];
+            uint32_t (&a1)[8] = v[ph][1];
+            ldg256(gplane + o0, *reinterpret_cast<uint32_t (*)[4]>(&a0[0]), *reinterpret_cast<uint32_t (*)[4]>(&a0[4]));
+            ldg256(gplane + o1, *reinterpret_cast<uint32_t (*)[4]>(&a1[0]), *reinterpret_cast<uint32_t (*)[4]>(&a1[4]));
+          }
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {
+            uint32_t mine[4];
+            if (!BF16) {
+              const __half2 wA = *reinterpret_cast<const __half2*>(&wsel[ph][0]), wB = *reinterpret_cast<const __half2*>(&wsel[ph][1]);
+              uint32_t part[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __half2 r = __hfma2(wB, *reinterpret_cast<const __half2*>(&v[ph][1][j]),
+                                          __hmul2(wA, *reinterpret_cast<const __half2*>(&v[ph][0][j])));
+                part[j] = *reinterpret_cast<const uint32_t*>(&r);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t send = s_slot ? part[j] : part[4 + j];
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                mine[j] = add2<false>(s_slot ? part[4 + j] : part[j], recv);
+              }
+            } else {
+              const float wA = __half2float(__ushort_as_half(static_cast<unsigned short>(wsel[ph][0] & 0xFFFFu)));
+              const float wB = __half2float(__ushort_as_half(static_cast<unsigned short>(wsel[ph][1] & 0xFFFFu)));
+              float part[16];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 f0 = unpack_bf16x2(v[ph][0][j]), f1 = unpack_bf16x2(v[ph][1][j]);
+                part[2 * j] = fmaf(wB, f1.x, wA * f0.x);
+                part[2 * j + 1] = fmaf(wB, f1.y, wA * f0.y);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float s0 = s_slot ? part[2 * j] : part[8 + 2 * j], s1 = s_slot ? part[2 * j + 1] : part[8 + 2 * j + 1];
+                const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                const float k0 = s_slot ? part[8 + 2 * j] : part[2 * j], k1 = s_slot ? part[8 + 2 * j + 1] : part[2 * j + 1];
+                mine[j] = pack_bf16x2(k0 + r0, k1 + r1);
+              }
+            }
+            const int prow = rq * 32 + 16 * ph + (lane >> 1);   // tile row (pixel) this lane pair produced
+            sts128(stage_base + prow * 128 + (((sub * 2 + s_slot) ^ (prow & 7)) << 4), mine[0], mine[1], mine[2], mine[3]);
           }
         }
         fence_proxy_async();
@@ -444,6 +533,7 @@ deform_conv_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&om_empty[os]);
         if (++os == kOmStages) { os = 0; ophase ^= 1; }
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -511,6 +601,11 @@ extern "C" int flair_deform_conv(const flair_deform_conv_params* p, void* stream
   a.stage_bytes = kABytes + a.b_bytes;
   a.mrm = p->max_residue_magnitude;
   a.fmt = (p->dtype == FLAIR_BF16) ? 1u : 0u;
+  {
+    static int coop = -1;   // FLAIR_DEFORM_COOP=0: one lane per sample everywhere (A/B measurements)
+    if (coop < 0) { const char* e = getenv("FLAIR_DEFORM_COOP"); coop = e ? atoi(e) : 1; }
+    a.coop = coop;
+  }
   // Shared memory is kept to ~128 KB so that the 132 KB carve-out leaves ~120 KB of L1: the gather re-reads every
   // source pixel ~36 times (9 taps x 4 corners) and with 16 x 8 tiles its working set is ~140 KB; with all 227 KB
   // given to the pipeline the L1 hit rate was 5 % and the kernel ran at the L2 bandwidth limit (958 MB / launch).
@@ -528,7 +623,7 @@ extern "C" int flair_deform_conv(const flair_deform_conv_params* p, void* stream
   // which only throttle on their own stage: with fewer stages than k-blocks per tap a fast warp can be two phases
   // ahead of the MMA on a stage, and a parity wait cannot tell "two phases ago" from "now" (it then overwrote a
   // stage that had not been consumed: non-deterministic results at C = 128 with 3 stages).
-  if (stages < a.kpt) stages = a.kpt;
+  // (all 16 gather warps fill the same k-block now, so the ring no longer has to hold a whole tap)
   FLAIR_REQUIRE(stages >= 2, "flair_deform_conv: tile does not fit shared memory");
   a.stages = stages;
   const size_t smem_bytes = static_cast<size_t>(stages) * a.stage_bytes + kOmStages * kOmBytes + 1024 + 512;
@@ -538,7 +633,7 @@ extern "C" int flair_deform_conv(const flair_deform_conv_params* p, void* stream
   const CUtensorMapDataType dt16 = (p->dtype == FLAIR_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap tmB, tmOM;
   {
-    // packed weight [1][C_pad16][18C] K-major (flair pack of the (C, 18C) matrix, k = tap*2C + channel)
+    // packed weight [1][C_pad16][18C] K-major, channel-block-major K: k = (kbq*9 + tap)*64 + c, kbq = 64-channel block of cat(xa, xb)
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(18 * p->C), static_cast<cuuint64_t>(p->C)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(18 * p->C) * 2};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(p->C)};

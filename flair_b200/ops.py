@@ -55,7 +55,7 @@ def pack_conv_weight(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
 
 
 def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, rowscale=None, residual=None, residual2=None, out=None,
-         out_dtype=None, act=L.ACT_NONE, stride=1, nchw_out=False, out_scale=1.0, out2=None, preadd=None):
+         out_dtype=None, act=L.ACT_NONE, stride=1, nchw_out=False, out_scale=1.0, out2=None, preadd=None, out2_neighbor=1):
     """Implicit-GEMM convolution (see flair_conv_igemm in include/flair_b200.h).
 
     x: [B,T,H,W,Cin] channels-last 16-bit; wpk: pack_conv_weight(...) output."""
@@ -106,6 +106,7 @@ def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, rowscale=Non
             and out2.stride(1) == 2 * out2.shape[3] and out2.dtype == out.dtype
         assert out2.shape[0] * out2.shape[3] == cout and out2.shape[1] == B * T * Ho * Wo
         p.out2 = _ptr(out2); p.out2_group_channels = out2.shape[3]; p.out2_group_stride = out2.stride(0)
+        p.out2_neighbor = int(out2_neighbor)
     L.check(L.lib().flair_conv_igemm(C.byref(p), _stream()))
     return out
 
@@ -451,13 +452,36 @@ def deform_offset_perm(deform_groups=16):
     return torch.tensor(perm, dtype=torch.long)
 
 
-def pair_planes(x):
-    """[N,H,W,C] channels-last map -> pair planes [8][N*H*W][2][C/8] (entry p = pixels p, p+1).  Torch ops: test /
-    setup helper; in the model the conv epilogue writes this layout directly (ops.conv(out2=...))."""
+def deform_weight_kperm(C):
+    """Column permutation of the (C, 9*2C) tap-major deformable weight (k = tap*2C + channel of cat(xa, xb)) into the
+    channel-block-major K order flair_deform_conv walks: k' = (kbq*9 + tap)*64 + c, kbq = 64-channel block."""
+    nkb = 2 * C // 64
+    k = torch.arange(9 * 2 * C).reshape(9, nkb, 64)          # [tap][kbq][c] -> old index
+    return k.permute(1, 0, 2).reshape(-1)
+
+
+def pack_deform_weight(w, dtype):
+    """w: (C, 2C, 3, 3) ModulatedDeformConv2d weight or its (C, 9*2C) tap-major matrix -> packed weight of
+    flair_deform_conv (channel-block-major K)."""
+    if w.dim() == 4:
+        w = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+    return pack_conv_weight(w.float()[:, deform_weight_kperm(w.shape[0]).to(w.device)], dtype)
+
+
+def pair_planes(x, vertical=False):
+    """[N,H,W,C] channels-last map -> pair planes [8][N*H*W][2][C/8].  Horizontal (what flair_deform_conv gathers from):
+    entry p = pixels (p, p+1) of the row-major map; vertical: entry (y,x) = pixels ((y,x), (y+1,x)).  Torch ops: test /
+    setup helper; in the model the conv epilogue writes this layout directly (ops.conv(out2=..., out2_neighbor=...))."""
     N, H, W, Cc = x.shape
     g = x.reshape(N * H * W, 8, Cc // 8).permute(1, 0, 2)
-    nxt = torch.cat([g[:, 1:], torch.zeros_like(g[:, :1])], 1)
+    d = W if vertical else 1
+    nxt = torch.cat([g[:, d:], torch.zeros_like(g[:, :d])], 1)
     return torch.stack([g, nxt], 2).contiguous()
+
+
+def pair_neighbor(C, W):
+    """out2_neighbor of the pair planes flair_deform_conv expects for C feature channels (horizontal pairs)."""
+    return 1
 
 
 def deform_conv(xa, xb, om, flow1, flow2, wpk, bias, mrm, *, out=None):

@@ -383,7 +383,8 @@ class ResidualBlocksWithInputConv(nn.Module, _Packed):
             last = i == len(pk["blocks"]) - 1
             t = ops.conv(x, w1, c, (1, 3, 3), bias=b1, act=L.ACT_RELU)
             x = ops.conv(t, w2, c, (1, 3, 3), bias=b2, residual=x, residual2=extra_residual if last else None,
-                         out=out if last else None, out2=out2 if last else None)
+                         out=out if last else None, out2=out2 if last else None,
+                         out2_neighbor=ops.pair_neighbor(c, x.shape[3]))
         return x
 
     def run(self, feat, dtype, extra_residual=None, out=None, out2=None):
@@ -456,7 +457,9 @@ class SecondOrderDeformableAlignment(ModulatedDeformConv2d, _Packed):
         split = dict(rec2=ops.pack_conv_weight(th.cat([w0[:, :oc], w0[:, 2 * oc:3 * oc]], 1), dtype),
                      rec1=ops.pack_conv_weight(w0[:, :oc], dtype),
                      static=ops.pack_conv_weight(th.cat([w0[:, oc:2 * oc], w0[:, 3 * oc:]], 1), dtype))
-        return dict(off=off, wd=ops.pack_conv_weight(wd, dtype), bd=_f(self.bias), split=split)
+        # fused kernel: channel-block-major K (ops.deform_weight_kperm); generic im2col + GEMM path: tap-major K
+        wd_pk = ops.pack_deform_weight(wd, dtype) if self.fused else ops.pack_conv_weight(wd, dtype)
+        return dict(off=off, wd=wd_pk, bd=_f(self.bias), split=split)
 
     @property
     def fused(self):
@@ -540,7 +543,8 @@ class BasicVSRPP(nn.Module, _Packed):
         wmap8 = wmap8n = None
         if wmap is not None:  # per-plane weight maps for the pair-plane copies (entry p: pixels p and p+1)
             wmap8 = wmap[:, None].expand(T, 8, H, W).contiguous()
-            wmap8n = th.roll(wmap.reshape(T, H * W), -1, 1).reshape(T, 1, H, W).expand(T, 8, H, W).contiguous()
+            # slot 1 of entry p is pixel p + neighbor (1: horizontal pairs at C = 128, W: vertical pairs at C = 64)
+            wmap8n = th.roll(wmap.reshape(T, H * W), -ops.pair_neighbor(C, W), 1).reshape(T, 1, H, W).expand(T, 8, H, W).contiguous()
         frames = hidden[0]  # [T,H,W,C]
         # reconstruction input for ALL frames: [spatial | backward feature | forward feature]; the two
         # propagation passes write their outputs straight into its channel slices
@@ -567,8 +571,8 @@ class BasicVSRPP(nn.Module, _Packed):
             prop = prev2 = prop_g = prev2_g = None
             fused = da.fused
             # pair-plane copies of the propagated features (written by the backbone's last conv): the layout the
-            # fused deformable conv gathers from; slot 1 of each plane's last entry is never written -> the buffer
-            # is persistent and zeroed once (it is read with weight 0, it only has to stay finite)
+            # fused deformable conv gathers from; slot 1 of each plane's last entry / last row is never written -> the
+            # buffer is persistent and zeroed once (it is read with weight 0, it only has to stay finite)
             gm_all = self._persistent(("gm", name, T, H, W, C, dt, str(dev)),
                                       lambda: th.zeros(T, 8, H * W, 2, C // 8, dtype=dt, device=dev)) if fused else None
             for i, idx in enumerate(order):

@@ -100,6 +100,9 @@ typedef struct flair_conv_params {
   /* [Cout/gc][B*T*H*W][2][gc], gc = out2_group_channels: entry p holds pixel  */
   /* p and pixel p+1 (row-major) — the source layout flair_deform_conv gathers */
   /* from (BasicVSR++ feat_prop).  Slot 1 of the last entry is never written.  */
+  /* out2_neighbor = d (0 means 1): slot 1 of entry p holds pixel p + d, i.e.  */
+  /* d = 1 pairs (x, x+1) (what flair_deform_conv gathers from), d = W pairs   */
+  /* (y, y+1); the last d entries' slot 1 is never written.                    */
   void* out2;
   int out2_group_channels;       /* 8 or 16                                   */
   long long out2_group_stride;   /* elements between group planes             */
@@ -113,6 +116,7 @@ typedef struct flair_conv_params {
   const void* preadd;
   int preadd_dtype;    /* FLAIR_BF16 / FLAIR_F32 / FLAIR_F16                  */
   int preadd_cstride;
+  int out2_neighbor;   /* see out2 (0 = 1)                                     */
 } flair_conv_params;
 
 int flair_conv_igemm(const flair_conv_params* p, void* stream);
@@ -324,18 +328,18 @@ int flair_scale_pixels(void* x, const float* wmap, long long pixels, int C, int 
  * flair_deform_im2col + flair_conv_igemm.
  *
  * Sources are pair planes [8 groups][N*H*W entries][2][C/8] (what flair_conv_igemm
- * writes through `out2`): entry p = (pixel p, pixel p+1) of the row-major map, so
- * the two x-corners of a bilinear sample are one aligned 32/64-byte load.  Element
- * (image n, group g, entry (y,x), slot s, channel c) lives at
+ * writes through `out2`).  Element (image n, group g, entry (y,x), slot s, channel c) lives at
  *   base + n*nstride + g*gstride + (y*W + x)*pstride + s*C/8 + c,  pstride = 2*C/8.
- * Slot 1 of the last entry of a plane must hold finite values (it is read with
- * weight 0).
+ * Entry p = (pixel p, pixel p+1) of the row-major map (out2_neighbor 1): the two x-corners of a bilinear sample are one
+ * aligned 32-byte (C = 64) / 64-byte (C = 128) entry; at C = 128 a lane pair fetches its two slots in one instruction.
+ * Never-written slots (slot 1 of the last entry / last row) must hold finite values (read with weight 0).
  * `om`: [N*H*W][om_cstride] fp16 (always, also with bf16 features) output of the offset net with its 432 channels
  * permuted to tap-major order: channel = tap*48 + quad*12 + kind*4 + gi for deform
  * group quad*4 + gi, kind 0 = dy, 1 = dx, 2 = mask (reference order: dy/dx at
  * (group*9 + tap)*2 + {0,1}, mask at 288 + group*9 + tap) — permute the rows of the
  * last offset conv's weight/bias once at pack time.
- * `wgt`: flair pack of the (C, 18C) matrix, k = tap*2C + channel of cat(xa, xb).
+ * `wgt`: flair pack of the (C, 18C) matrix in channel-block-major K order: k = (kbq*9 + tap)*64 + c, kbq = 64-channel
+ *   block of cat(xa, xb) (all nine taps of a block are gathered back to back: its source planes stay in L1).
  * ---------------------------------------------------------------------- */
 typedef struct flair_deform_conv_params {
   const void* xa; long long xa_gstride, xa_pstride, xa_nstride;

@@ -17,7 +17,7 @@ if smooth:
     f1, f2 = sm(f1, 15), sm(f2, 15)
 w = (torch.randn(C, 2 * C, 3, 3, generator=g) / (18 * C) ** 0.5); b = torch.randn(C, generator=g) * 0.1
 om_p = o.half()[..., ops.deform_offset_perm()].contiguous().to(dev)
-wpk = ops.pack_conv_weight(w.permute(0, 2, 3, 1).reshape(C, -1), dt).to(dev)
+wpk = ops.pack_deform_weight(w, dt).to(dev)
 gm = ops.pair_planes
 xa_g, xb_g, f1d, f2d, bd = gm(xa.to(dev)), gm(xb.to(dev)), f1.to(dev), f2.to(dev), b.to(dev)
 out = torch.empty(N, H, W, C, dtype=dt, device=dev)

@@ -32,7 +32,7 @@ def run(C, H, W, N=1, dt=torch.float16, mrm=10.0, time_it=False, smooth=False):
     perm = ops.deform_offset_perm()
     om_p = o[..., perm].contiguous().to(dev)
     wd = w.permute(0, 2, 3, 1).reshape(C, -1)
-    wpk = ops.pack_conv_weight(wd, dt).to(dev)
+    wpk = ops.pack_deform_weight(wd, dt).to(dev)
     xa_d, xb_d, f1d, f2d, bd = xa.to(dev), xb.to(dev), f1.to(dev), f2.to(dev), b.to(dev)
     xa_g, xb_g = ops.pair_planes(xa_d), ops.pair_planes(xb_d)
     out = ops.deform_conv(xa_g, xb_g, om_p, f1d, f2d, wpk, bd, mrm)

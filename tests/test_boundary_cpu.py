@@ -160,6 +160,14 @@ def test_deform_offset_permutation_and_pair_planes():
     assert torch.equal(P[:, :, 0], flat.permute(1, 0, 2))                    # slot 0: pixel p
     assert torch.equal(P[:, :-1, 1], flat.permute(1, 0, 2)[:, 1:])           # slot 1: pixel p+1 (row-major, across rows/images)
     assert float(P[:, -1, 1].abs().max()) == 0.0                             # last entry: zeros
+    V = ops.pair_planes(x, vertical=True)                                    # C = 64 layout: slot 1 = pixel p + W
+    assert torch.equal(V[:, :, 0], flat.permute(1, 0, 2)) and torch.equal(V[:, :-4, 1], flat.permute(1, 0, 2)[:, 4:])
+    assert float(V[:, -4:, 1].abs().max()) == 0.0
+    # channel-block-major K order of the fused kernel's weight: k' = (kbq*9 + tap)*64 + c  <-  k = tap*2C + kbq*64 + c
+    kp = ops.deform_weight_kperm(64)
+    assert sorted(kp.tolist()) == list(range(9 * 128))
+    for kbq, tap, c in [(0, 0, 0), (1, 0, 5), (0, 8, 63), (1, 4, 17)]:
+        assert int(kp[(kbq * 9 + tap) * 64 + c]) == tap * 128 + kbq * 64 + c
 
 
 # ------------------------------------------------------------------------------------------------ demo script (f1 / f4)

@@ -86,9 +86,10 @@ def test_conv_pair_plane_output(dev, C, H):
     wide = torch.zeros(1, 1, H, H, 3 * C, dtype=torch.float16, device=dev)
     out = wide[..., C:2 * C]
     P = torch.full((8, H * H, 2, C // 8), 7.0, dtype=torch.float16, device=dev)
-    ops.conv(x, wpk, C, (1, 3, 3), out=out, out2=P)
-    ref = ops.pair_planes(out[0].contiguous())
-    ref[:, -1, 1] = 7.0  # slot 1 of the last entry is never written
+    nb = H if H == 40 else 1   # one case with vertical pairs (neighbor = W); flair_deform_conv uses horizontal ones
+    ops.conv(x, wpk, C, (1, 3, 3), out=out, out2=P, out2_neighbor=nb)
+    ref = ops.pair_planes(out[0].contiguous(), vertical=nb != 1)
+    ref[:, -nb:, 1] = 7.0  # slot 1 of the last `neighbor` entries is never written
     assert torch.equal(P, ref)
     assert float(wide[..., :C].abs().max()) == 0.0 and float(wide[..., 2 * C:].abs().max()) == 0.0
 
@@ -209,7 +210,7 @@ def test_deform_conv_fused(dev, C, H, W, N, dt):
     nchw = lambda t: t.float().permute(0, 3, 1, 2)
     ref = K.deform_align_core(nchw(xa), nchw(xb), nchw(o), f1, f2, w, b, 10.0).permute(0, 2, 3, 1)
     om = o[..., ops.deform_offset_perm()].contiguous().to(dev)
-    wpk = ops.pack_conv_weight(w.float().permute(0, 2, 3, 1).reshape(C, -1), dt).to(dev)
+    wpk = ops.pack_deform_weight(w.float(), dt).to(dev)
     xa_p, xb_p = ops.pair_planes(xa.to(dev)), ops.pair_planes(xb.to(dev))
     wide = torch.zeros(N, H, W, 2 * C, dtype=dt, device=dev)
     y1 = ops.deform_conv(xa_p, xb_p, om, f1.to(dev), f2.to(dev), wpk, b.to(dev), 10.0, out=wide[..., C:]).clone()
@@ -228,11 +229,13 @@ def test_deform_conv_matches_two_kernel_path(dev):
     xa, xb = torch.randn(1, H, W, C, generator=g).half().to(dev), torch.randn(1, H, W, C, generator=g).half().to(dev)
     o = (torch.randn(1, H, W, 432, generator=g) * 0.5).half().to(dev)
     f1, f2 = (torch.randn(1, 2, H, W, generator=g) * 2).to(dev), (torch.randn(1, 2, H, W, generator=g) * 3).to(dev)
-    wpk = ops.pack_conv_weight(torch.randn(C, 18 * C, generator=g) / (18 * C) ** 0.5, torch.float16).to(dev)
+    w2d = torch.randn(C, 18 * C, generator=g) / (18 * C) ** 0.5
+    wpk = ops.pack_conv_weight(w2d, torch.float16).to(dev)          # tap-major K (im2col + GEMM path)
+    wpk_f = ops.pack_deform_weight(w2d, torch.float16).to(dev)      # channel-block-major K (fused kernel)
     cols = ops.deform_im2col(xa, xb, o, f1, f2, 16, 10.0)
     old = ops.conv(cols, wpk, C, (1, 1, 1))[0]
     new = ops.deform_conv(ops.pair_planes(xa), ops.pair_planes(xb), o[..., ops.deform_offset_perm().to(dev)].contiguous(),
-                          f1, f2, wpk, None, 10.0)
+                          f1, f2, wpk_f, None, 10.0)
     assert _rel(new, old) < 1e-3
 
 
