@@ -90,8 +90,10 @@ struct ConvKArgs {
   int act;
   float out_scale;
   uint32_t fmt;
-  float* gn_partial;
+  float* gn_partial;       // fused GroupNorm statistics of the OUTPUT: [m_tile][4 lane quarters][Cout_pad/16][16] floats
   int gn_groups;
+  int gn_cpg;              // channels per group (power of two >= 2)
+  int gn_nchunks;          // Cout_pad / 16
   int fast;                // compact epilogue applies (see epilogue_fast): 1 = no addends, 2 = addends prefetched
   uint16_t* out2;          // optional copy of a 16-bit NHWC output as pair planes [Cout/out2_gs][pixels][2][out2_gs]:
   int out2_gs;             // entry p = (pixel p, pixel p+1), the source layout of flair_deform_conv
@@ -341,11 +343,62 @@ __device__ __forceinline__ void add16(float (&v)[16], const uint4 (&u2)[2], bool
   }
 }
 
+// Sum N values per lane over the 32 lanes of a warp with N - 1 + (5 - log2 N) shuffles (halving butterfly): at every step
+// a lane keeps one half of its values and receives the partner's copy of that half.  Afterwards lane l holds the total
+// of value index (l >> (5 - log2 N)) in x[0].  Fixed order -> deterministic.
+template <int N>
+__device__ __forceinline__ float warp_sum_n(float (&x)[N], int lane) {
+  int n = N;
+#pragma unroll
+  for (int mask = 16; mask >= 1; mask >>= 1) {
+    if (n > 1) {
+      const int half = n >> 1;
+      const bool up = (lane & mask) != 0;
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i) {
+        if (i < half) {
+          const float send = up ? x[i] : x[i + half];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, mask);
+          x[i] = (up ? x[i + half] : x[i]) + recv;
+        }
+      }
+      n = half;
+    } else {
+      x[0] += __shfl_xor_sync(0xffffffffu, x[0], mask);
+    }
+  }
+  return x[0];
+}
+
+// GroupNorm statistics of one stored 16-channel chunk (values as rounded to the 16-bit output, zero for rows outside
+// the map): per group of `cpg` channels inside the chunk (sum, sum of squares) over the warp's 32 pixels ->
+// slot[2*g], slot[2*g+1] (cpg > 16: the chunk is part of one group -> slot[0], slot[1]).
+template <int NG>
+__device__ __forceinline__ void gn_chunk_stats(const float (&vr)[16], float* __restrict__ slot, int lane) {
+  constexpr int CPG = 16 / NG;
+  float x[2 * NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPG; ++j) {
+      const float t = vr[g * CPG + j];
+      sm += t;
+      sq = fmaf(t, t, sq);
+    }
+    x[2 * g] = sm;
+    x[2 * g + 1] = sq;
+  }
+  const float tot = warp_sum_n<2 * NG>(x, lane);
+  constexpr int SH = (NG == 8) ? 1 : (NG == 4) ? 2 : (NG == 2) ? 3 : 4;   // lane l holds value index l >> SH
+  if ((lane & ((1 << SH) - 1)) == 0) slot[lane >> SH] = tot;
+}
+
 // one 16-column chunk: bias, [preadd], activation, [scale], [residuals], pack, one 32-byte store (+ pair planes)
 // mask: bit 0 preadd (slot A), bit 1 residual (slot B), bit 2 residual2 (slot A)
 __device__ __forceinline__ void fast_chunk(const ConvKArgs& a, const uint32_t (&r)[16], int c0, int n, long long pix,
                                            bool valid, const float* __restrict__ sb, const uint4 (&pa)[2],
-                                           const uint4 (&pb)[2], int mask, bool f16) {
+                                           const uint4 (&pb)[2], int mask, bool f16, float* __restrict__ gn_tile) {
   float v[16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -372,7 +425,6 @@ __device__ __forceinline__ void fast_chunk(const ConvKArgs& a, const uint32_t (&
   }
   if (mask & 2) add16(v, pb, f16);
   if (mask & 4) add16(v, pa, f16);
-  if (!valid) return;
   uint32_t u[8];
   if (f16) {
 #pragma unroll
@@ -384,6 +436,25 @@ __device__ __forceinline__ void fast_chunk(const ConvKArgs& a, const uint32_t (&
 #pragma unroll
     for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
   }
+  if (gn_tile != nullptr) {
+    // fused GroupNorm statistics of the tensor being stored (nn_new.py:17-19 computes them on the stored 16-bit map)
+    float vr[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 f;
+      if (f16) f = __half22float2(*reinterpret_cast<const __half2*>(&u[j]));
+      else f = unpack_bf16x2(u[j]);
+      vr[2 * j] = valid ? f.x : 0.f;
+      vr[2 * j + 1] = valid ? f.y : 0.f;
+    }
+    float* slot = gn_tile + (n >> 4) * 16;
+    const int lane = threadIdx.x & 31;
+    if (a.gn_cpg == 2) gn_chunk_stats<8>(vr, slot, lane);
+    else if (a.gn_cpg == 4) gn_chunk_stats<4>(vr, slot, lane);
+    else if (a.gn_cpg == 8) gn_chunk_stats<2>(vr, slot, lane);
+    else gn_chunk_stats<1>(vr, slot, lane);
+  }
+  if (!valid) return;
   uint16_t* op = static_cast<uint16_t*>(a.out) + pix * a.out_cstride + n;
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
                "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
@@ -404,7 +475,7 @@ __device__ __forceinline__ void fast_chunk(const ConvKArgs& a, const uint32_t (&
 template <bool PF>
 __device__ __forceinline__ void epilogue_fast(const ConvKArgs& a, uint32_t t_addr, int col_begin, int col_end, int n0,
                                               long long pix, bool valid, const float* __restrict__ sb,
-                                              const EpiPrefetch& pf, int mask, bool f16) {
+                                              const EpiPrefetch& pf, int mask, bool f16, float* __restrict__ gn_tile) {
   if (PF) {
 #pragma unroll
     for (int cp = 0; cp < kPfChunks / 2; ++cp) {
@@ -415,8 +486,8 @@ __device__ __forceinline__ void epilogue_fast(const ConvKArgs& a, uint32_t t_add
         tmem_ld16(t_addr + static_cast<uint32_t>(cc), r0);
         tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);
         tmem_ld_wait();
-        fast_chunk(a, r0, cc, n0 + cc, pix, valid, sb, pf.a[2 * cp], pf.b[2 * cp], mask, f16);
-        if (cc + 16 < col_end) fast_chunk(a, r1, cc + 16, n0 + cc + 16, pix, valid, sb, pf.a[2 * cp + 1], pf.b[2 * cp + 1], mask, f16);
+        fast_chunk(a, r0, cc, n0 + cc, pix, valid, sb, pf.a[2 * cp], pf.b[2 * cp], mask, f16, gn_tile);
+        if (cc + 16 < col_end) fast_chunk(a, r1, cc + 16, n0 + cc + 16, pix, valid, sb, pf.a[2 * cp + 1], pf.b[2 * cp + 1], mask, f16, gn_tile);
       }
     }
   } else {
@@ -428,8 +499,8 @@ __device__ __forceinline__ void epilogue_fast(const ConvKArgs& a, uint32_t t_add
       tmem_ld16(t_addr + static_cast<uint32_t>(cc), r0);
       tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);
       tmem_ld_wait();
-      fast_chunk(a, r0, cc, n0 + cc, pix, valid, sb, none, none, 0, f16);
-      if (cc + 16 < col_end) fast_chunk(a, r1, cc + 16, n0 + cc + 16, pix, valid, sb, none, none, 0, f16);
+      fast_chunk(a, r0, cc, n0 + cc, pix, valid, sb, none, none, 0, f16, gn_tile);
+      if (cc + 16 < col_end) fast_chunk(a, r1, cc + 16, n0 + cc + 16, pix, valid, sb, none, none, 0, f16, gn_tile);
     }
   }
 }
@@ -834,6 +905,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t acc_phase = (local >> 1) & 1;
       int m_idx, n_idx;
       tile_at(local, m_idx, n_idx);
+      float* gn_tile = (a.gn_partial != nullptr)
+                           ? a.gn_partial + (static_cast<long long>(m_idx) * 4 + quarter) * a.gn_nchunks * 16 : nullptr;
       const int tw = m_idx % a.tiles_w; m_idx /= a.tiles_w;
       const int th = m_idx % a.tiles_h; m_idx /= a.tiles_h;
       const int tt = m_idx % a.tiles_t;
@@ -896,9 +969,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       } else if (a.fast == 2) {
-        epilogue_fast<true>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, pf_mask, a.out_dtype == FLAIR_F16);
+        epilogue_fast<true>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, pf_mask, a.out_dtype == FLAIR_F16, gn_tile);
       } else if (a.fast == 1) {
-        epilogue_fast<false>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, 0, a.out_dtype == FLAIR_F16);
+        epilogue_fast<false>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, 0, a.out_dtype == FLAIR_F16, gn_tile);
       } else
       switch (kind * 4 + a.act) {
 #define EPI_CASE(K, A) case (K) * 4 + (A): epilogue_cols<K, A>(a, t_addr, col_begin, col_end, pos, sb); break;
@@ -963,6 +1036,23 @@ extern "C" int flair_debug_conv_trace(long long* host_out16) {
   return 0;
 }
 
+// Number of M tiles (and M tiles per batch element) flair_conv_igemm walks for these extents: sizes the gn_partial
+// buffer of the fused GroupNorm statistics ([m_tiles][4][Cout/16][16] floats).  Mirrors the tile selection below.
+extern "C" int flair_conv_gn_tiles(int B, int T, int H, int W, int kh, int kw, int stride_hw, int* m_tiles,
+                                   int* tiles_per_batch) {
+  FLAIR_REQUIRE(m_tiles && tiles_per_batch && B > 0 && T > 0 && H > 0 && W > 0 && (stride_hw == 1 || stride_hw == 2),
+                "flair_conv_gn_tiles: bad arguments");
+  const int s = stride_hw;
+  const int Ho = (H + s - 1) / s, Wo = (W + s - 1) / s;
+  int bw = pow2_ceil(Wo); if (bw > kBlockM) bw = kBlockM;
+  int bh = pow2_ceil(Ho); if (bh > kBlockM / bw) bh = kBlockM / bw;
+  int bt = kBlockM / (bw * bh);
+  if (kh == 3 && kw == 3 && s == 1 && Wo >= 8 && Ho >= 16 && flair_conv_mode_override() != 0) { bw = 8; bh = 16; bt = 1; }
+  *tiles_per_batch = ceil_div(Wo, bw) * ceil_div(Ho, bh) * ceil_div(T, bt);
+  *m_tiles = *tiles_per_batch * B;
+  return 0;
+}
+
 extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FLAIR_REQUIRE(p != nullptr, "flair_conv_igemm: null params");
@@ -987,7 +1077,6 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
     FLAIR_REQUIRE(p->out_dtype == FLAIR_F32, "flair_conv_igemm: NCHW output is fp32 only");
   else
     FLAIR_REQUIRE(p->out_cstride >= p->Cout, "flair_conv_igemm: out_cstride < Cout");
-  FLAIR_REQUIRE(p->gn_partial == nullptr, "flair_conv_igemm: fused GN partials not enabled yet");
 
   const int s = p->stride_hw;
   const int Ho = (p->H + s - 1) / s, Wo = (p->W + s - 1) / s;
@@ -1101,6 +1190,18 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
     static int fast_env = -1;
     if (fast_env < 0) { const char* e = getenv("FLAIR_CONV_FAST_EPI"); fast_env = e ? atoi(e) : 1; }
     a.fast = (!plain || !fast_env) ? 0 : (!any_add ? 1 : ((add_ok && same_dt) ? 2 : 0));
+  }
+  if (p->gn_partial != nullptr) {
+    const int cpg = (p->gn_groups > 0 && p->Cout % p->gn_groups == 0) ? p->Cout / p->gn_groups : 0;
+    FLAIR_REQUIRE(cpg >= 2 && (cpg & (cpg - 1)) == 0 && (cpg <= 16 || cpg % 16 == 0),
+                  "flair_conv_igemm: fused GN statistics need a power-of-two group size >= 2 (Cout=%d groups=%d)", p->Cout,
+                  p->gn_groups);
+    if (a.fast == 0) {  // nothing was launched: the caller falls back to flair_gn_stats
+      flair_set_error("flair_conv_igemm: fused GN statistics need the compact epilogue (16-bit NHWC output, Cout %% 16 == 0, "
+                      "no per-frame bias / gate, 16-bit aligned addends)");
+      return FLAIR_ERR_UNSUPPORTED;
+    }
+    a.gn_partial = p->gn_partial; a.gn_groups = p->gn_groups; a.gn_cpg = cpg; a.gn_nchunks = Cout_pad / 16;
   }
   a.out2 = static_cast<uint16_t*>(p->out2); a.out2_gs = p->out2_group_channels; a.out2_gstride = p->out2_group_stride;
   a.out2_nb = p->out2_neighbor > 0 ? p->out2_neighbor : 1;

@@ -188,6 +188,75 @@ gn_stats_kernel(const void* __restrict__ x, int dtype, long long P, int C, int c
   if (threadIdx.x == 0) counter[b] = 0;  // self-cleaning: the next launch on this stream finds zeros
 }
 
+// ---------------------------------------------------------------- statistics fused into the producing conv
+// flair_conv_igemm (gn_partial) leaves [B*tpb][4][nch][16] floats: per M tile, per 32-row quarter, per 16-channel chunk
+// the (sum, sum of squares) of every group inside the chunk (cpg <= 16: floats 2g, 2g+1; cpg > 16: floats 0, 1 of each
+// of the group's chunks).  Stage 1 (grid (nsplit, B)): column sums over a contiguous range of entries, in double,
+// fixed order.  Stage 2: the LAST block of a batch element (ticket) adds the splits in order and writes (mean, rstd)
+// in the format gn_apply reads (nchunks = 0).  Deterministic; replaces the 2 B/element statistics pass.
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float* __restrict__ partial, int entries, int cols, int cpg, int groups, double count,
+                   double* __restrict__ scratch, int* __restrict__ counter, float2* __restrict__ final_stats, float eps) {
+  pdl_sync();
+  extern __shared__ double sred[];   // [rows][cols]
+  const int b = blockIdx.y, sp = blockIdx.x, nsplit = gridDim.x;
+  const int per = (entries + nsplit - 1) / nsplit;
+  const int e0 = sp * per, e1 = min(entries, e0 + per);
+  const int rows = (cols >= 256) ? 1 : 256 / cols;
+  const float* base = partial + static_cast<long long>(b) * entries * cols;
+  for (int f0 = 0; f0 < cols; f0 += 256) {
+    const int f = f0 + static_cast<int>(threadIdx.x) % min(cols, 256);
+    const int r = (cols >= 256) ? 0 : static_cast<int>(threadIdx.x) / cols;
+    double acc = 0.0;
+    if (f < cols && r < rows) {
+      int e = e0 + r;
+      for (; e + 3 * rows < e1; e += 4 * rows) {   // 4 loads in flight, summed in entry order
+        const float v0 = __ldcg(base + static_cast<long long>(e) * cols + f);
+        const float v1 = __ldcg(base + static_cast<long long>(e + rows) * cols + f);
+        const float v2 = __ldcg(base + static_cast<long long>(e + 2 * rows) * cols + f);
+        const float v3 = __ldcg(base + static_cast<long long>(e + 3 * rows) * cols + f);
+        acc += v0; acc += v1; acc += v2; acc += v3;
+      }
+      for (; e < e1; e += rows) acc += __ldcg(base + static_cast<long long>(e) * cols + f);
+      sred[r * cols + f] = acc;
+    }
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < cols; f += blockDim.x) {
+    double a = 0.0;
+    for (int r = 0; r < rows; ++r) a += sred[r * cols + f];
+    scratch[(static_cast<long long>(b) * nsplit + sp) * cols + f] = a;
+  }
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter + b, 1) == nsplit - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double sd = 0.0, qd = 0.0;
+    const int c_first = g * cpg;
+    const int nparts = (cpg > 16) ? cpg / 16 : 1;
+    for (int part = 0; part < nparts; ++part) {
+      const int chunk = c_first / 16 + part;
+      const int idx = (cpg > 16) ? 0 : (c_first % 16) / cpg;
+      const int fs = chunk * 16 + 2 * idx;
+      for (int k = 0; k < nsplit; ++k) {
+        const double* row = scratch + (static_cast<long long>(b) * nsplit + k) * cols;
+        sd += __ldcg(row + fs);
+        qd += __ldcg(row + fs + 1);
+      }
+    }
+    const double mean = sd / count;
+    double var = qd / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    final_stats[static_cast<long long>(b) * groups + g] =
+        make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+  }
+  if (threadIdx.x == 0) counter[b] = 0;  // self-cleaning
+}
+
 struct ApplyArgs {
   const void* x; int in_dtype;
   void* out; int out_dtype;
@@ -492,6 +561,33 @@ extern "C" int flair_gn_stats(const void* x, int dtype, int B, long long P, int 
   FLAIR_CHECK_CUDA(flair_launch(gn_stats_kernel, dim3(grid), dim3(vecs * ppb), smem, stream, x, dtype, P, C, cstride, groups, ppb, ppc,
                                 reinterpret_cast<float2*>(partial), counter, reinterpret_cast<float2*>(final_stats),
                                 eps > 0 ? eps : 1e-5f));
+  FLAIR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int flair_gn_finalize_splits(int tiles_per_batch) {
+  int n = (tiles_per_batch * 4) / 64;
+  if (n < 1) n = 1;
+  if (n > 32) n = 32;
+  return n;
+}
+
+extern "C" int flair_gn_finalize(const float* partial, int B, int tiles_per_batch, int C, int groups,
+                                 long long pixels_per_batch, double* scratch, int* counter, float* final_stats,
+                                 float eps, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FLAIR_REQUIRE(partial && scratch && counter && final_stats, "flair_gn_finalize: null pointer");
+  FLAIR_REQUIRE(B > 0 && B < 65536 && tiles_per_batch > 0 && C % 16 == 0 && C <= 2048 && groups > 0 && groups <= kGroupsMax &&
+                    C % groups == 0,
+                "flair_gn_finalize: bad arguments (C=%d groups=%d)", C, groups);
+  const int cpg = C / groups;
+  FLAIR_REQUIRE(cpg >= 2 && (cpg & (cpg - 1)) == 0 && (cpg <= 16 || cpg % 16 == 0), "flair_gn_finalize: unsupported group size %d", cpg);
+  const int nsplit = flair_gn_finalize_splits(tiles_per_batch);
+  const int rows = (C >= 256) ? 1 : 256 / C;
+  const size_t smem = sizeof(double) * rows * C;
+  FLAIR_CHECK_CUDA(flair_launch(gn_finalize_kernel, dim3(nsplit, B), dim3(256), smem, stream, partial, tiles_per_batch * 4, C, cpg,
+                                groups, static_cast<double>(pixels_per_batch) * cpg, scratch, counter,
+                                reinterpret_cast<float2*>(final_stats), eps > 0 ? eps : 1e-5f));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }

@@ -8,6 +8,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -55,7 +57,8 @@ def pack_conv_weight(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
 
 
 def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, rowscale=None, residual=None, residual2=None, out=None,
-         out_dtype=None, act=L.ACT_NONE, stride=1, nchw_out=False, out_scale=1.0, out2=None, preadd=None, out2_neighbor=1):
+         out_dtype=None, act=L.ACT_NONE, stride=1, nchw_out=False, out_scale=1.0, out2=None, preadd=None, out2_neighbor=1,
+         gn_groups=None):
     """Implicit-GEMM convolution (see flair_conv_igemm in include/flair_b200.h).
 
     x: [B,T,H,W,Cin] channels-last 16-bit; wpk: pack_conv_weight(...) output."""
@@ -107,7 +110,33 @@ def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, rowscale=Non
         assert out2.shape[0] * out2.shape[3] == cout and out2.shape[1] == B * T * Ho * Wo
         p.out2 = _ptr(out2); p.out2_group_channels = out2.shape[3]; p.out2_group_stride = out2.stride(0)
         p.out2_neighbor = int(out2_neighbor)
-    L.check(L.lib().flair_conv_igemm(C.byref(p), _stream()))
+    gn = None
+    if gn_groups and FUSED_GN and not nchw_out and out.dtype != torch.float32 and cout % 16 == 0 and cout % gn_groups == 0:
+        # GroupNorm statistics of the output from the conv's own epilogue (flair_conv_params.gn_partial): the next
+        # norm then needs no statistics pass over the map.  Only when every M tile lies inside one batch element.
+        mt, tpb = C.c_int(0), C.c_int(0)
+        L.check(L.lib().flair_conv_gn_tiles(B, T, H, W, kh, kw, stride, C.byref(mt), C.byref(tpb)))
+        Bo = out.shape[0]
+        if mt.value % (Bo * (out.shape[1] if kt == 1 else 1)) == 0 or Bo == 1:
+            gn = dict(groups=gn_groups, tpb=mt.value // Bo,
+                      partial=torch.empty(mt.value * 4 * cout, dtype=torch.float32, device=x.device))
+            p.gn_partial = _ptr(gn["partial"]); p.gn_groups = gn_groups
+    rc = L.lib().flair_conv_igemm(C.byref(p), _stream())
+    if rc == -3 and gn is not None:  # no compact epilogue for this launch (nothing ran): plain conv, separate statistics
+        gn = None
+        p.gn_partial = None; p.gn_groups = 0
+        rc = L.lib().flair_conv_igemm(C.byref(p), _stream())
+    L.check(rc)
+    if gn is not None:
+        Bo, To = out.shape[0], out.shape[1]
+        nsplit = L.lib().flair_gn_finalize_splits(gn["tpb"])
+        scratch = torch.empty(Bo * nsplit * cout, dtype=torch.float64, device=x.device)
+        fin = torch.empty(Bo, gn_groups, 2, dtype=torch.float32, device=x.device)
+        L.check(L.lib().flair_gn_finalize(_ptr(gn["partial"]), Bo, gn["tpb"], cout, gn_groups, To * Ho * Wo, _ptr(scratch),
+                                          _ptr(_gn_counter(x.device, Bo)), _ptr(fin), 1e-5, _stream()))
+        out._flair_gn = (gn_groups, out.data_ptr(), (fin, 0))
+    elif hasattr(out, "_flair_gn"):
+        del out._flair_gn   # `out` was a reused buffer: its old statistics are stale
     return out
 
 
@@ -289,10 +318,16 @@ def _gn_counter(device, B):
     return c
 
 
+FUSED_GN = os.environ.get("FLAIR_FUSED_GN", "1") != "0"   # A/B switch: 0 = always run the separate statistics kernel
+
+
 def gn_stats(x, groups=32, eps=1e-5):
     """GroupNorm statistics over (T,H,W,C/G) per batch element.  Returns (final, 0): final[b][g] = (mean, rstd),
     reduced deterministically by the last CTA of the launch (see flair_gn_stats); gn_apply takes the pair as is."""
     B, T, H, W, Cc = x.shape
+    fused = getattr(x, "_flair_gn", None)   # left by ops.conv(gn_groups=...) on the tensor it produced
+    if fused is not None and fused[0] == groups and fused[1] == x.data_ptr() and eps == 1e-5 and FUSED_GN:
+        return fused[2]
     P = T * H * W
     n = L.lib().flair_gn_stats_chunks(P, Cc)
     counter = _gn_counter(x.device, B)

@@ -45,12 +45,15 @@ from .nn_new import avg_pool_nd, conv_nd, linear, normalization, timestep_embedd
 # --------------------------------------------------------------------------------------------------
 class _Ctx:
     """dtype: GEMM operand type (bf16/fp16); sdtype: storage type of the residual stream."""
-    __slots__ = ("emb_all", "flows", "weights", "cross", "dtype", "T", "sdtype", "emb_plain", "gates")
+    __slots__ = ("emb_all", "flows", "weights", "cross", "dtype", "T", "sdtype", "emb_plain", "gates", "gn_next", "gn_tail")
 
     def __init__(self, emb_all, flows, weights, cross, dtype, T, sdtype=None):
         self.emb_all, self.flows, self.weights, self.cross, self.dtype, self.T = emb_all, flows, weights, cross, dtype, T
         self.sdtype = sdtype or dtype
         self.emb_plain = self.gates = None  # sr3: un-activated noise embeddings / sigmoid gates
+        # gn_next: the tensor a module is about to produce is consumed by a GroupNorm next (its producing conv then
+        # leaves the statistics, ops.conv(gn_groups=...)); gn_tail: the same for the last module of a block
+        self.gn_next, self.gn_tail = False, True
 
     def operand(self, x):
         """A 16-bit GEMM-operand copy of a residual-stream map (no-op when the stream is already 16-bit)."""
@@ -113,14 +116,18 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
     """Sequential with type-based argument routing (reference :106-133)."""
 
     def forward(self, x, ctx):
+        run = []
         for layer in self:
             if isinstance(layer, TemporalWrapper):
                 if ctx.cross:
-                    x = layer.wrapped_module(x, ctx)
-            elif isinstance(layer, nn.Identity):
-                pass
-            else:
-                x = layer(x, ctx)
+                    run.append(layer.wrapped_module)
+            elif not isinstance(layer, nn.Identity):
+                run.append(layer)
+        for i, layer in enumerate(run):
+            # every module but BasicVSR++ (and the first conv) starts with a GroupNorm of its input
+            ctx.gn_next = ctx.gn_tail if i + 1 == len(run) else not isinstance(run[i + 1], BasicVSRPP)
+            x = layer(x, ctx)
+        ctx.gn_next = False
         return x
 
 
@@ -208,7 +215,7 @@ class ResBlock(TimestepBlock, _Packed):
         a1 = ops.gn_apply(x, ops.gn_stats(x), pk["g1"], pk["be1"], silu=True, resample=self._resample,
                           out_dtype=ctx.dtype)
         if self.use_scale_shift_norm:
-            h1 = ops.conv(a1, pk["w1"], cout, ks, bias=pk["b1"])
+            h1 = ops.conv(a1, pk["w1"], cout, ks, bias=pk["b1"], gn_groups=32)   # statistics of out_layers' norm
             a2 = ops.gn_apply(h1, ops.gn_stats(h1), pk["g2"], pk["be2"], scale=emb[:, :cout], shift=emb[:, cout:],
                               silu=True)
         else:  # h + emb_out, then norm (reference :326-328)
@@ -221,7 +228,8 @@ class ResBlock(TimestepBlock, _Packed):
             xs = ops.conv(xs, pk["ws"], cout, (1, 1, 1) if kk[-1] == 1 else ks, bias=pk["bs"], out_dtype=ctx.sdtype)
         else:
             xs = ops.gn_apply(x, None, resample=self._resample) if self.updown else x
-        return ops.conv(a2, pk["w2"], cout, ks, bias=pk["b2"], residual=xs, rowscale=gate, out_dtype=ctx.sdtype)
+        return ops.conv(a2, pk["w2"], cout, ks, bias=pk["b2"], residual=xs, rowscale=gate, out_dtype=ctx.sdtype,
+                        gn_groups=32 if ctx.gn_next else None)
 
 
 class _AttnBase(_Packed):
@@ -249,13 +257,16 @@ class _AttnBase(_Packed):
         return dict(g=_f(n.weight), b=_f(n.bias), wqkv=_w(self.qkv, dtype), bqkv=_f(self.qkv.bias),
                     wp=_w(self.proj_out, dtype), bp=_f(self.proj_out.bias))
 
+    _gn_next_hint = False
+
     def _attend(self, x, rowbias, dtype):
         pk = self.packed(dtype)
         c = self.channels
         a = ops.gn_apply(x, ops.gn_stats(x), pk["g"], pk["b"], out_dtype=dtype)
         qkv = ops.conv(a, pk["wqkv"], 3 * c, (1, 1, 1), bias=pk["bqkv"])
         att = ops.attn_spatial(qkv, self.num_heads, rowbias=rowbias)
-        return ops.conv(att, pk["wp"], c, (1, 1, 1), bias=pk["bp"], residual=x, out_dtype=x.dtype)
+        return ops.conv(att, pk["wp"], c, (1, 1, 1), bias=pk["bp"], residual=x, out_dtype=x.dtype,
+                        gn_groups=32 if self._gn_next_hint else None)
 
 
 class AttentionBlock(nn.Module, _AttnBase):
@@ -267,6 +278,7 @@ class AttentionBlock(nn.Module, _AttnBase):
         self._init_attn(channels, num_heads, num_head_channels, use_checkpoint, use_new_attention_order)
 
     def forward(self, x, ctx):
+        self._gn_next_hint = ctx.gn_next
         return self._attend(x, None, ctx.dtype)
 
 
@@ -282,6 +294,7 @@ class AttentionbottleBlock(TimestepBlock, _AttnBase):
 
     def forward(self, x, ctx):
         off, width = self._emb_slot
+        self._gn_next_hint = ctx.gn_next
         return self._attend(x, ctx.emb_all[:, off:off + width], ctx.dtype)
 
 
@@ -339,7 +352,8 @@ class TemporalAttention(nn.Module, _Packed):
         x = ops.gn_apply(h, ops.gn_stats(h), pk["g"], pk["b"], out_dtype=ctx.dtype)
         qkv = ops.conv(x, pk["wqkv"], 3 * c, (1, 1, 1))
         att = ops.attn_temporal(qkv, pk["cq"], pk["ck"], pk["bv"], self.num_frames)
-        return ops.conv(att, pk["wp"], c, (1, 1, 1), bias=pk["bp"], residual=h, rowscale=gate, out_dtype=h.dtype)
+        return ops.conv(att, pk["wp"], c, (1, 1, 1), bias=pk["bp"], residual=h, rowscale=gate, out_dtype=h.dtype,
+                        gn_groups=32 if ctx.gn_next else None)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -527,6 +541,7 @@ class BasicVSRPP(nn.Module, _Packed):
                            w[b:b + 1] if th.is_tensor(w) else w, ctx.cross, ctx.dtype, ctx.T, ctx.sdtype)
                 outs.append(self.forward(hidden[b:b + 1], sub, None if gate is None else gate[b * T_:(b + 1) * T_]))
             return th.cat(outs, 0)
+        gn_next = ctx.gn_next         # (the sub-module calls below do not go through a Sequential)
         stream = hidden               # residual-stream copy (may be fp32): only the final add reads it
         hidden = ctx.operand(hidden)  # 16-bit operand copy: features / warps / convs
         _, T, H, W, C = hidden.shape
@@ -605,7 +620,7 @@ class BasicVSRPP(nn.Module, _Packed):
         pk_last = self.packed(ctx.dtype)
         rec = self.reconstruction.run(rec_cat, ctx.dtype)
         return ops.conv(rec, pk_last[0], C, (1, 1, 1), bias=pk_last[1], residual=stream, rowscale=gate,
-                        out_dtype=stream.dtype)
+                        out_dtype=stream.dtype, gn_groups=32 if gn_next else None)
 
     def _persistent(self, key, make):
         """Module-owned buffers that outlive a forward (allocated during the eager warm-up that precedes every
@@ -968,13 +983,15 @@ class UNetModel(nn.Module):
             self._in_stamp = st
         packed = ops.pack_im2col6(x, low_res_input.reshape(N, 3, H, W), dt).view(B, T, H, W, 64)
         h = ops.conv(packed, self._in_pk[0], conv_in.out_channels, (1, 1, 1), bias=self._in_pk[1],
-                     out_dtype=self.stream_dtype)
+                     out_dtype=self.stream_dtype, gn_groups=32)
+        ctx.gn_tail = True
         hs = [h]
         for block in list(self.input_blocks)[1:]:
             h = block(h, ctx)
             hs.append(h)
         h = self.middle_block(h, ctx)
-        for block in self.output_blocks:
+        for i, block in enumerate(self.output_blocks):
+            ctx.gn_tail = i + 1 == len(self.output_blocks)   # other outputs go through a channel concat first
             h = block(ops.concat_channels(h, hs.pop()), ctx)
         n_out, c_out = self.out[0].wrapped_module, self.out[2].wrapped_module
         st = (dt, c_out.weight.data_ptr(), c_out.weight._version)

@@ -93,9 +93,16 @@ typedef struct flair_conv_params {
   int act;             /* FLAIR_ACT_*; applied before the residual add        */
   int in_dtype;        /* FLAIR_BF16 or FLAIR_F16 (x and wgt)                 */
   float out_scale;     /* multiplies the result after act, before residual    */
-  /* optional fused GroupNorm statistics of the OUTPUT (for the next norm):   */
-  float* gn_partial;   /* NULL, or [B*T][gn_groups][2] fp32 sums, atomically  */
-  int gn_groups;       /* accumulated (sum, sum of squares)                   */
+  /* optional fused GroupNorm statistics of the OUTPUT (for the next norm,    */
+  /* nn_new.py:17-19): NULL, or [m_tiles][4][Cout/16][16] fp32 written by the  */
+  /* epilogue — per M tile, 32-row quarter and 16-channel chunk the (sum, sum  */
+  /* of squares) of every group of Cout/gn_groups channels in the chunk, of    */
+  /* the values as stored (16-bit).  m_tiles from flair_conv_gn_tiles; reduced */
+  /* to (mean, rstd) by flair_gn_finalize (deterministic, no atomics on data). */
+  /* Needs the compact epilogue: 16-bit NHWC output, Cout % 16 == 0, no        */
+  /* rowbias / rowscale, 16-bit addends; group size a power of two >= 2.       */
+  float* gn_partial;
+  int gn_groups;
   /* optional second copy of a 16-bit NHWC output as "pair planes"            */
   /* [Cout/gc][B*T*H*W][2][gc], gc = out2_group_channels: entry p holds pixel  */
   /* p and pixel p+1 (row-major) — the source layout flair_deform_conv gathers */
@@ -120,6 +127,7 @@ typedef struct flair_conv_params {
 } flair_conv_params;
 
 int flair_conv_igemm(const flair_conv_params* p, void* stream);
+int flair_conv_gn_tiles(int B, int T, int H, int W, int kh, int kw, int stride_hw, int* m_tiles, int* tiles_per_batch);
 /* debug: in a library built with -DFLAIR_CONV_TRACE_BUILD and run with FLAIR_CONV_TRACE=1, CTA 0 of every conv
  * launch records clock64() at 15 points (see conv_igemm.cu); copies the 16 values of the most recent launch to
  * the host (synchronises).  All zeros in a normal build. */
@@ -257,6 +265,12 @@ typedef struct flair_gn_apply_params {
   float eps;
 } flair_gn_apply_params;
 int flair_gn_apply(const flair_gn_apply_params* p, void* stream);
+/* Statistics left by flair_conv_igemm (gn_partial) -> final[b][g] = (mean, rstd) as flair_gn_apply reads them with
+ * nchunks = 0.  scratch: [B][flair_gn_finalize_splits(tiles_per_batch)][C] doubles; counter: [B] ints, zero on entry
+ * (self-cleaning, may be shared with flair_gn_stats).  pixels_per_batch = T*H*W of the normalised map. */
+int flair_gn_finalize_splits(int tiles_per_batch);
+int flair_gn_finalize(const float* partial, int B, int tiles_per_batch, int C, int groups, long long pixels_per_batch,
+                      double* scratch, int* counter, float* final_stats, float eps, void* stream);
 /* dst[p][dst_coffset + c] = src[p][c]: channel concat (th.cat(dim=2), unet_new.py:1359). */
 int flair_copy_channels(const void* src, void* dst, long long pixels, int channels, int elem_bytes,
                         int src_cstride, int dst_cstride, int dst_coffset, void* stream);

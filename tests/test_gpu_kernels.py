@@ -94,6 +94,38 @@ def test_conv_pair_plane_output(dev, C, H):
     assert float(wide[..., :C].abs().max()) == 0.0 and float(wide[..., 2 * C:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("B,T,H,Cin,C,ks,groups,res", [(1, 3, 32, 64, 64, (1, 3, 3), 32, False), (1, 2, 32, 64, 128, (1, 3, 3), 32, True),
+                                                       (4, 1, 16, 128, 256, (1, 3, 3), 32, True), (1, 4, 8, 256, 512, (1, 1, 1), 32, True),
+                                                       (2, 3, 16, 64, 64, (3, 3, 3), 32, False), (1, 2, 16, 128, 1024, (1, 3, 3), 16, False),
+                                                       (3, 1, 4, 64, 64, (1, 3, 3), 32, False)])
+def test_conv_fused_group_norm_statistics(dev, B, T, H, Cin, C, ks, groups, res):
+    """flair_conv_params.gn_partial + flair_gn_finalize: the (mean, rstd) left by the conv epilogue equal the
+    statistics kernel's on the stored output (group sizes 2..64, 3x3 / 1x1 / 3x3x3, residual, several batch elements;
+    the last case has M tiles spanning frames of different batch elements -> ops.conv falls back, no attribute)."""
+    from flair_b200 import ops
+    g = torch.Generator().manual_seed(C + H + B)
+    x = torch.randn(B, T, H, H, Cin, generator=g).half().to(dev)
+    w = torch.randn(C, Cin, *ks, generator=g) / (Cin * ks[0] * ks[1] * ks[2]) ** 0.5
+    wpk = ops.pack_conv_weight(w, torch.float16).to(dev)
+    r = torch.randn(B, T, H, H, C, generator=g).half().to(dev) if res else None
+    y = ops.conv(x, wpk, C, ks, bias=torch.randn(C, generator=g).to(dev), residual=r, gn_groups=groups)
+    y_plain = ops.conv(x, wpk, C, ks, bias=torch.randn(C, generator=torch.Generator().manual_seed(C + H + B)).to(dev) * 0, residual=r)
+    fused = getattr(y, "_flair_gn", None)
+    if B == 3:
+        assert fused is None   # 4x4 maps: one 128-pixel tile holds 8 frames = several batch elements
+        return
+    assert fused is not None and fused[0] == groups
+    fin = fused[2][0]
+    delattr(y, "_flair_gn")
+    ref = ops.gn_stats(y, groups)[0]   # the statistics kernel on the same stored map
+    assert torch.allclose(fin[..., 0], ref[..., 0], rtol=0, atol=2e-5 * float(ref[..., 0].abs().max() + 1))
+    assert torch.allclose(fin[..., 1], ref[..., 1], rtol=2e-5, atol=0)
+    # deterministic: a second launch leaves the same bits
+    y2 = ops.conv(x, wpk, C, ks, bias=None, residual=r, gn_groups=groups)
+    y3 = ops.conv(x, wpk, C, ks, bias=None, residual=r, gn_groups=groups)
+    assert torch.equal(y2._flair_gn[2][0], y3._flair_gn[2][0]) and y_plain.shape == y.shape
+
+
 @pytest.mark.parametrize("C,groups,T,H,dt", [(64, 32, 3, 32, torch.float16), (256, 32, 2, 8, torch.bfloat16),
                                               (128, 16, 4, 16, torch.float16), (192, 32, 2, 16, torch.float16)])
 def test_group_norm_film_silu(dev, C, groups, T, H, dt):
