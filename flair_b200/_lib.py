@@ -101,9 +101,10 @@ def lib() -> C.CDLL:
         _lib.flair_gn_stats_chunks.argtypes = [ll, i]
         _lib.flair_gn_stats.argtypes = [vp, i, i, ll, i, i, i, vp, i, vp, vp, f, vp]
         _lib.flair_gn_apply.argtypes = [C.POINTER(GNApplyParams), vp]
-        _lib.flair_conv_gn_tiles.argtypes = [i, i, i, i, i, i, i, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-        _lib.flair_gn_finalize_splits.argtypes = [i]
-        _lib.flair_gn_finalize.argtypes = [vp, i, i, i, i, ll, vp, vp, vp, f, vp]
+        if hasattr(_lib, "flair_gn_finalize"):  # (absent from an older A/B library given through FLAIR_B200_LIB)
+            _lib.flair_conv_gn_tiles.argtypes = [i, i, i, i, i, i, i, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+            _lib.flair_gn_finalize_splits.argtypes = [i]
+            _lib.flair_gn_finalize.argtypes = [vp, i, i, i, i, ll, vp, vp, vp, f, vp]
         _lib.flair_copy_channels.argtypes = [vp, vp, ll, i, i, i, i, i, vp]
         _lib.flair_attn_spatial.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, vp]
         _lib.flair_attn_temporal.argtypes = [vp, vp, vp, vp, vp, i, i, ll, i, i, i, vp]

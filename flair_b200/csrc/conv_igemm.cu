@@ -396,6 +396,7 @@ __device__ __forceinline__ void gn_chunk_stats(const float (&vr)[16], float* __r
 
 // one 16-column chunk: bias, [preadd], activation, [scale], [residuals], pack, one 32-byte store (+ pair planes)
 // mask: bit 0 preadd (slot A), bit 1 residual (slot B), bit 2 residual2 (slot A)
+template <bool GN>
 __device__ __forceinline__ void fast_chunk(const ConvKArgs& a, const uint32_t (&r)[16], int c0, int n, long long pix,
                                            bool valid, const float* __restrict__ sb, const uint4 (&pa)[2],
                                            const uint4 (&pb)[2], int mask, bool f16, float* __restrict__ gn_tile) {
@@ -436,8 +437,9 @@ __device__ __forceinline__ void fast_chunk(const ConvKArgs& a, const uint32_t (&
 #pragma unroll
     for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
   }
-  if (gn_tile != nullptr) {
-    // fused GroupNorm statistics of the tensor being stored (nn_new.py:17-19 computes them on the stored 16-bit map)
+  if (GN) {
+    // fused GroupNorm statistics of the tensor being stored (a separate instantiation: with this code in the plain
+    // path every N = 64 launch was 8 % slower, profiles/r02_summary.md) (nn_new.py:17-19 computes them on the stored 16-bit map)
     float vr[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -472,7 +474,7 @@ __device__ __forceinline__ void fast_chunk(const ConvKArgs& a, const uint32_t (&
 }
 
 // PF: addends are in registers (<= 4 chunks per warp, chunk index compile-time)
-template <bool PF>
+template <bool PF, bool GN>
 __device__ __forceinline__ void epilogue_fast(const ConvKArgs& a, uint32_t t_addr, int col_begin, int col_end, int n0,
                                               long long pix, bool valid, const float* __restrict__ sb,
                                               const EpiPrefetch& pf, int mask, bool f16, float* __restrict__ gn_tile) {
@@ -486,8 +488,8 @@ __device__ __forceinline__ void epilogue_fast(const ConvKArgs& a, uint32_t t_add
         tmem_ld16(t_addr + static_cast<uint32_t>(cc), r0);
         tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);
         tmem_ld_wait();
-        fast_chunk(a, r0, cc, n0 + cc, pix, valid, sb, pf.a[2 * cp], pf.b[2 * cp], mask, f16, gn_tile);
-        if (cc + 16 < col_end) fast_chunk(a, r1, cc + 16, n0 + cc + 16, pix, valid, sb, pf.a[2 * cp + 1], pf.b[2 * cp + 1], mask, f16, gn_tile);
+        fast_chunk<GN>(a, r0, cc, n0 + cc, pix, valid, sb, pf.a[2 * cp], pf.b[2 * cp], mask, f16, gn_tile);
+        if (cc + 16 < col_end) fast_chunk<GN>(a, r1, cc + 16, n0 + cc + 16, pix, valid, sb, pf.a[2 * cp + 1], pf.b[2 * cp + 1], mask, f16, gn_tile);
       }
     }
   } else {
@@ -499,8 +501,8 @@ __device__ __forceinline__ void epilogue_fast(const ConvKArgs& a, uint32_t t_add
       tmem_ld16(t_addr + static_cast<uint32_t>(cc), r0);
       tmem_ld16(t_addr + static_cast<uint32_t>(cc + 16), r1);
       tmem_ld_wait();
-      fast_chunk(a, r0, cc, n0 + cc, pix, valid, sb, none, none, 0, f16, gn_tile);
-      if (cc + 16 < col_end) fast_chunk(a, r1, cc + 16, n0 + cc + 16, pix, valid, sb, none, none, 0, f16, gn_tile);
+      fast_chunk<GN>(a, r0, cc, n0 + cc, pix, valid, sb, none, none, 0, f16, gn_tile);
+      if (cc + 16 < col_end) fast_chunk<GN>(a, r1, cc + 16, n0 + cc + 16, pix, valid, sb, none, none, 0, f16, gn_tile);
     }
   }
 }
@@ -540,6 +542,11 @@ constexpr int kMaxStages = 8;
 // the epilogue warps 4, 8 / 5, 9 pre-empted them and the tensor pipe drained (round 2: -30 % on N = 64 launches).
 constexpr int kWarpTma = 8, kWarpMma = 9;
 
+// EPI: which epilogues are compiled into the instance.  0 = all (generic (kind x activation) template + compact paths),
+// 1 = compact paths only, 2 = compact paths with the fused GroupNorm statistics only.  The generic template is ~43 K of
+// the kernel's ~50 K instructions; a per-frame launch fetches its code cold (conv, deformable conv and warp launches
+// alternate on the BasicVSR++ chain), so the 1300 per-frame launches of a forward run a 4-6 K-instruction instance.
+template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvKArgs a) {
@@ -968,11 +975,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (r0[0] == 0x7fc12345u && pos.valid) static_cast<uint16_t*>(a.out)[0] = 0;  // keep the load alive
           }
         }
-      } else if (a.fast == 2) {
-        epilogue_fast<true>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, pf_mask, a.out_dtype == FLAIR_F16, gn_tile);
-      } else if (a.fast == 1) {
-        epilogue_fast<false>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, 0, a.out_dtype == FLAIR_F16, gn_tile);
-      } else
+      } else if (EPI == 2) {   // host: fast != 0 and gn_partial != NULL
+        if (a.fast == 2)
+          epilogue_fast<true, true>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, pf_mask, a.out_dtype == FLAIR_F16, gn_tile);
+        else
+          epilogue_fast<false, true>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, 0, a.out_dtype == FLAIR_F16, gn_tile);
+      } else if (EPI == 1 || a.fast != 0) {   // (EPI == 1: host guarantees fast != 0, no statistics)
+        if (a.fast == 2)
+          epilogue_fast<true, false>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, pf_mask, a.out_dtype == FLAIR_F16, nullptr);
+        else
+          epilogue_fast<false, false>(a, t_addr, col_begin, col_end, pos.n0, pos.pix, pos.valid, sb, pf, 0, a.out_dtype == FLAIR_F16, nullptr);
+      } else if (EPI == 0)
       switch (kind * 4 + a.act) {
 #define EPI_CASE(K, A) case (K) * 4 + (A): epilogue_cols<K, A>(a, t_addr, col_begin, col_end, pos, sb); break;
         EPI_CASE(0, 0) EPI_CASE(0, 1) EPI_CASE(0, 2) EPI_CASE(0, 3)
@@ -1039,8 +1052,9 @@ extern "C" int flair_debug_conv_trace(long long* host_out16) {
 // Number of M tiles (and M tiles per batch element) flair_conv_igemm walks for these extents: sizes the gn_partial
 // buffer of the fused GroupNorm statistics ([m_tiles][4][Cout/16][16] floats).  Mirrors the tile selection below.
 extern "C" int flair_conv_gn_tiles(int B, int T, int H, int W, int kh, int kw, int stride_hw, int* m_tiles,
-                                   int* tiles_per_batch) {
-  FLAIR_REQUIRE(m_tiles && tiles_per_batch && B > 0 && T > 0 && H > 0 && W > 0 && (stride_hw == 1 || stride_hw == 2),
+                                   int* tiles_per_batch, int* frames_per_tile) {
+  FLAIR_REQUIRE(m_tiles && tiles_per_batch && frames_per_tile && B > 0 && T > 0 && H > 0 && W > 0 &&
+                    (stride_hw == 1 || stride_hw == 2),
                 "flair_conv_gn_tiles: bad arguments");
   const int s = stride_hw;
   const int Ho = (H + s - 1) / s, Wo = (W + s - 1) / s;
@@ -1050,6 +1064,7 @@ extern "C" int flair_conv_gn_tiles(int B, int T, int H, int W, int kh, int kw, i
   if (kh == 3 && kw == 3 && s == 1 && Wo >= 8 && Ho >= 16 && flair_conv_mode_override() != 0) { bw = 8; bh = 16; bt = 1; }
   *tiles_per_batch = ceil_div(Wo, bw) * ceil_div(Ho, bh) * ceil_div(T, bt);
   *m_tiles = *tiles_per_batch * B;
+  *frames_per_tile = bt;
   return 0;
 }
 
@@ -1269,9 +1284,11 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
   }
 
   static FlairPerDeviceOnce attr_once;
-  if (attr_once.first())
-    FLAIR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+  if (attr_once.first()) {
+    FLAIR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    FLAIR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    FLAIR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+  }
   const int total_tiles = a.m_tiles * a.n_tiles;
   int grid = flair_num_sms();
   if (grid > total_tiles) grid = total_tiles;
@@ -1279,7 +1296,14 @@ extern "C" int flair_conv_igemm(const flair_conv_params* p, void* stream_) {
     grid = (grid / a.n_tiles) * a.n_tiles;
     if (grid < a.n_tiles) grid = a.n_tiles;
   }
-  FLAIR_CHECK_CUDA(flair_launch(conv_igemm_kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, a));
+  static int slim = -1;   // FLAIR_CONV_SLIM=0: always launch the full instance (A/B measurements)
+  if (slim < 0) { const char* e = getenv("FLAIR_CONV_SLIM"); slim = e ? atoi(e) : 1; }
+  if (slim && a.fast != 0 && a.gn_partial != nullptr)
+    FLAIR_CHECK_CUDA(flair_launch(conv_igemm_kernel<2>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, a));
+  else if (slim && a.fast != 0)
+    FLAIR_CHECK_CUDA(flair_launch(conv_igemm_kernel<1>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, a));
+  else
+    FLAIR_CHECK_CUDA(flair_launch(conv_igemm_kernel<0>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, a));
   FLAIR_CHECK_LAUNCH();
   return 0;
 }

@@ -20,16 +20,46 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // at 0.9 TB/s).  Each output still accumulates its taps in (u, v) order: bit-identical to the simple version.
 constexpr int kTileH = 16, kTileW = 64, kOutPerThread = 4;
 
-// stage rows [i0, i0 + span_h) x cols [j0, j0 + span_w) of one plane (replicate padding) into shared memory:
-// one warp per row, lanes along the row (coalesced, no divisions)
+// stage rows [i0, i0 + span_h) x cols [j0, j0 + span_w) of one plane (replicate padding) into shared memory.
+// The in-map part of every row is read with 16-byte loads, four rows per warp in flight (a 16 x 64 LR tile of the
+// x4 blur needs 72 full 256-pixel rows: with one 4-byte load per lane and 4 in flight the CTA kept ~4 KB outstanding
+// and blur_down ran at 1.06 TB/s, profiles/r02_hbm_probe.txt); the replicated border columns are filled afterwards.
 __device__ __forceinline__ void stage_tile(const float* __restrict__ xp, float* __restrict__ s_in, int i0, int j0,
                                            int span_h, int span_w, int pitch, int H, int W) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int ii = warp; ii < span_h; ii += nwarps) {
-    const float* rp = xp + static_cast<long long>(clampi(i0 + ii, 0, H - 1)) * W;
-    float* sp = s_in + ii * pitch;
-#pragma unroll 4
-    for (int jj = lane; jj < span_w; jj += 32) sp[jj] = __ldg(rp + clampi(j0 + jj, 0, W - 1));
+  const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(xp) & 15) == 0;
+  // in-map columns [ja, jb) of the span; their 16-byte aligned core [ja4, jb4)
+  const int ja = j0 > 0 ? j0 : 0, jb = (j0 + span_w < W) ? j0 + span_w : W;
+  int ja4 = (ja + 3) & ~3, jb4 = jb & ~3;
+  if (!vec_ok || jb4 <= ja4) { ja4 = ja; jb4 = ja; }   // no vector core
+  const int nvec = (jb4 - ja4) >> 2;
+  constexpr int kRows = 4;
+  for (int ii0 = warp * kRows; ii0 < span_h; ii0 += nwarps * kRows) {
+    for (int v = lane; v < nvec; v += 32) {
+      float4 raw[kRows];
+#pragma unroll
+      for (int q = 0; q < kRows; ++q) {
+        const int ii = ii0 + q;
+        if (ii < span_h)
+          raw[q] = __ldg(reinterpret_cast<const float4*>(xp + static_cast<long long>(clampi(i0 + ii, 0, H - 1)) * W + ja4) + v);
+      }
+#pragma unroll
+      for (int q = 0; q < kRows; ++q) {
+        const int ii = ii0 + q;
+        if (ii < span_h) {
+          float* sp = s_in + ii * pitch + (ja4 - j0) + 4 * v;   // (not 16-byte aligned in general)
+          sp[0] = raw[q].x; sp[1] = raw[q].y; sp[2] = raw[q].z; sp[3] = raw[q].w;
+        }
+      }
+    }
+  }
+  // everything outside the vector core: left part [0, ja4 - j0), right part [jb4 - j0, span_w)
+  const int left = ja4 - j0, right0 = jb4 - j0;
+  const int rest = left + (span_w - right0);
+  for (int idx = threadIdx.x; idx < span_h * rest; idx += blockDim.x) {
+    const int ii = idx / rest, k = idx - ii * rest;
+    const int jj = k < left ? k : right0 + (k - left);
+    s_in[ii * pitch + jj] = __ldg(xp + static_cast<long long>(clampi(i0 + ii, 0, H - 1)) * W + clampi(j0 + jj, 0, W - 1));
   }
 }
 

@@ -210,12 +210,12 @@ gn_finalize_kernel(const float* __restrict__ partial, int entries, int cols, int
     double acc = 0.0;
     if (f < cols && r < rows) {
       int e = e0 + r;
-      for (; e + 3 * rows < e1; e += 4 * rows) {   // 4 loads in flight, summed in entry order
-        const float v0 = __ldcg(base + static_cast<long long>(e) * cols + f);
-        const float v1 = __ldcg(base + static_cast<long long>(e + rows) * cols + f);
-        const float v2 = __ldcg(base + static_cast<long long>(e + 2 * rows) * cols + f);
-        const float v3 = __ldcg(base + static_cast<long long>(e + 3 * rows) * cols + f);
-        acc += v0; acc += v1; acc += v2; acc += v3;
+      for (; e + 7 * rows < e1; e += 8 * rows) {   // 8 loads in flight, summed in entry order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(base + static_cast<long long>(e + u * rows) * cols + f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
       }
       for (; e < e1; e += rows) acc += __ldcg(base + static_cast<long long>(e) * cols + f);
       sred[r * cols + f] = acc;
@@ -234,6 +234,23 @@ gn_finalize_kernel(const float* __restrict__ partial, int entries, int cols, int
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // stage 2: column sums over the splits (8 loads in flight, split order), then per group
+  __syncthreads();
+  for (int f = threadIdx.x; f < cols; f += blockDim.x) {
+    double a = 0.0;
+    const double* col = scratch + static_cast<long long>(b) * nsplit * cols + f;
+    int k = 0;
+    for (; k + 8 <= nsplit; k += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(col + static_cast<long long>(k + u) * cols);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += v[u];
+    }
+    for (; k < nsplit; ++k) a += __ldcg(col + static_cast<long long>(k) * cols);
+    sred[f] = a;
+  }
+  __syncthreads();
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double sd = 0.0, qd = 0.0;
     const int c_first = g * cpg;
@@ -242,11 +259,8 @@ gn_finalize_kernel(const float* __restrict__ partial, int entries, int cols, int
       const int chunk = c_first / 16 + part;
       const int idx = (cpg > 16) ? 0 : (c_first % 16) / cpg;
       const int fs = chunk * 16 + 2 * idx;
-      for (int k = 0; k < nsplit; ++k) {
-        const double* row = scratch + (static_cast<long long>(b) * nsplit + k) * cols;
-        sd += __ldcg(row + fs);
-        qd += __ldcg(row + fs + 1);
-      }
+      sd += sred[fs];
+      qd += sred[fs + 1];
     }
     const double mean = sd / count;
     double var = qd / count - mean * mean;
@@ -566,9 +580,9 @@ extern "C" int flair_gn_stats(const void* x, int dtype, int B, long long P, int 
 }
 
 extern "C" int flair_gn_finalize_splits(int tiles_per_batch) {
-  int n = (tiles_per_batch * 4) / 64;
+  int n = (tiles_per_batch * 4) / 32;   // >= 32 entries per block, up to 2 blocks per SM
   if (n < 1) n = 1;
-  if (n > 32) n = 32;
+  if (n > 296) n = 296;
   return n;
 }
 

@@ -69,38 +69,55 @@ __device__ __forceinline__ float up_at(const UpdArgs& a, const float* q, int i, 
   return acc;
 }
 
-// Up(q) for the FLAIR blur operator (scale factor 4, 9 x 9 taps): same taps in the same order as up_at, but the
-// polyphase indices are shifts / masks and the <= 3 x 3 contributing taps are a fully unrolled loop over taps
-// staged in shared memory (the generic version spent ~40 integer instructions per tap: 0.8 TB/s for the update).
-__device__ __forceinline__ float up_at_sf4k9(const UpdArgs& a, const float* __restrict__ s_taps, const float* q, int i, int j) {
-  constexpr int SF = 4, K = 9, r = 4;
+// Up(q) for the FLAIR blur operator (scale factor 4, 9 x 9 taps, 0 <= pre < 4) for the FOUR adjacent outputs
+// (i, j..j+3), j % 4 == 0, of one thread.  Same taps in the same (u, v) order as up_at (skipped taps enter as exact
+// zeros), but: the <= 3 x 3 contributing taps of every polyphase (u0, v0) come from a phase-major table in shared
+// memory (s_tp[u0][v0][3][3], zero where u or v >= 9), and the four outputs share ONE 3 x 4 patch of q held in
+// registers (12 loads per thread instead of 36 predicated ones; the per-output version ran the fused update at
+// 1.9 TB/s, issue-bound: profiles/r02_hbm_probe.txt).
+__device__ __forceinline__ void up4_sf4k9(const UpdArgs& a, const float* __restrict__ s_tp, const float* __restrict__ q,
+                                          int i, int j, float (&out)[4]) {
   const int h = a.H >> 2, w = a.W >> 2;
-  const int u0 = (a.pre + r - i) & 3, v0 = (a.pre + r - j) & 3;
-  float acc = 0.0f;
+  const int u0 = (a.pre + 4 - i) & 3;
+  const int mb = (i + u0 - 4 - a.pre) >> 2;  // LR row of tap row u0 (exact: the numerator is a multiple of 4)
+  const int nb = (j >> 2) - 1;               // LR column of the left-most contributing tap of output j
+  float Q[3][4];
 #pragma unroll
   for (int uu = 0; uu < 3; ++uu) {
-    const int u = u0 + uu * SF;
-    const int zi = i + u - r;
-    const int m = (zi - a.pre) >> 2;  // exact: zi - pre is a multiple of 4 by construction of u0
-    if (u < K && zi >= 0 && zi < a.H && m >= 0 && m < h) {
+    const int m = mb + uu;
+    const bool row_ok = m >= 0 && m < h;
 #pragma unroll
-      for (int vv = 0; vv < 3; ++vv) {
-        const int v = v0 + vv * SF;
-        const int zj = j + v - r;
-        const int n = (zj - a.pre) >> 2;
-        if (v < K && zj >= 0 && zj < a.W && n >= 0 && n < w) acc = fmaf(s_taps[u * K + v], __ldg(q + m * w + n), acc);
-      }
+    for (int cc = 0; cc < 4; ++cc) {
+      const int n = nb + cc;
+      Q[uu][cc] = (row_ok && n >= 0 && n < w) ? __ldg(q + m * w + n) : 0.0f;
     }
   }
-  return acc;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int v0 = (a.pre - k) & 3;
+    const bool off = ((k + v0 - a.pre) >> 2) != 0;  // first contributing LR column: nb (+1)
+    const float* tp = s_tp + (u0 * 4 + v0) * 9;
+    float acc = 0.0f;
+#pragma unroll
+    for (int uu = 0; uu < 3; ++uu) {
+#pragma unroll
+      for (int vv = 0; vv < 3; ++vv) acc = fmaf(tp[uu * 3 + vv], off ? Q[uu][vv + 1] : Q[uu][vv], acc);
+    }
+    out[k] = acc;
+  }
 }
 
 __global__ void __launch_bounds__(256) sampler_update_kernel(const __grid_constant__ UpdArgs a) {
   pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
-  __shared__ float s_taps[81];
-  const bool fast_up = a.q_lr != nullptr && a.sf == 4 && a.kk == 9;
+  __shared__ float s_tp[144];  // [u0][v0][uu][vv] = taps[u0 + 4 uu][v0 + 4 vv] (0 outside the 9 x 9 support)
+  const bool fast_up = a.q_lr != nullptr && a.sf == 4 && a.kk == 9 && a.pre >= 0 && a.pre < 4 && (a.W & 3) == 0 &&
+                       (a.H & 3) == 0;
   if (fast_up) {
-    if (threadIdx.x < 81) s_taps[threadIdx.x] = __ldg(a.up_taps + threadIdx.x);
+    if (threadIdx.x < 144) {
+      const int ph = threadIdx.x / 9, r = threadIdx.x - ph * 9;
+      const int u = (ph >> 2) + 4 * (r / 3), v = (ph & 3) + 4 * (r % 3);
+      s_tp[threadIdx.x] = (u < 9 && v < 9) ? __ldg(a.up_taps + u * 9 + v) : 0.0f;
+    }
     __syncthreads();
   }
   const long long hw = static_cast<long long>(a.H) * a.W;
@@ -140,9 +157,10 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(const __grid_consta
       const int i = static_cast<int>(off / a.W), j = static_cast<int>(off % a.W);
       const float* q = a.q_lr + plane * (hw / (a.sf * a.sf));
       if (fast_up) {
+        float up[4];
+        up4_sf4k9(a, s_tp, q, i, j, up);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          x0[k] = clampf(__fsub_rn(x0[k], __fmul_rn(gamma, up_at_sf4k9(a, s_taps, q, i, j + k))), a.clip);
+        for (int k = 0; k < 4; ++k) x0[k] = clampf(__fsub_rn(x0[k], __fmul_rn(gamma, up[k])), a.clip);
       } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)

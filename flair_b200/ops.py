@@ -114,10 +114,13 @@ def conv(x, wpk, cout, ksize=(1, 3, 3), *, bias=None, rowbias=None, rowscale=Non
     if gn_groups and FUSED_GN and not nchw_out and out.dtype != torch.float32 and cout % 16 == 0 and cout % gn_groups == 0:
         # GroupNorm statistics of the output from the conv's own epilogue (flair_conv_params.gn_partial): the next
         # norm then needs no statistics pass over the map.  Only when every M tile lies inside one batch element.
-        mt, tpb = C.c_int(0), C.c_int(0)
-        L.check(L.lib().flair_conv_gn_tiles(B, T, H, W, kh, kw, stride, C.byref(mt), C.byref(tpb)))
+        mt, tpb, fpt = C.c_int(0), C.c_int(0), C.c_int(0)
+        L.check(L.lib().flair_conv_gn_tiles(B, T, H, W, kh, kw, stride, C.byref(mt), C.byref(tpb), C.byref(fpt)))
         Bo = out.shape[0]
-        if mt.value % (Bo * (out.shape[1] if kt == 1 else 1)) == 0 or Bo == 1:
+        # (2-D kernels run with the frames of all batch elements flattened: a tile of `fpt` consecutive frames stays
+        # inside one batch element iff T % fpt == 0 — a rule that does not depend on the batch size, so a frame gets
+        # the same bits whether it is run alone or in a batch)
+        if kt == 3 or out.shape[1] % fpt.value == 0:
             gn = dict(groups=gn_groups, tpb=mt.value // Bo,
                       partial=torch.empty(mt.value * 4 * cout, dtype=torch.float32, device=x.device))
             p.gn_partial = _ptr(gn["partial"]); p.gn_groups = gn_groups

@@ -127,7 +127,10 @@ typedef struct flair_conv_params {
 } flair_conv_params;
 
 int flair_conv_igemm(const flair_conv_params* p, void* stream);
-int flair_conv_gn_tiles(int B, int T, int H, int W, int kh, int kw, int stride_hw, int* m_tiles, int* tiles_per_batch);
+/* M tiles flair_conv_igemm walks for these extents (sizes gn_partial), tiles per batch element of the call, and the
+ * number of consecutive frames one tile spans (> 1 on maps smaller than 128 pixels). */
+int flair_conv_gn_tiles(int B, int T, int H, int W, int kh, int kw, int stride_hw, int* m_tiles, int* tiles_per_batch,
+                        int* frames_per_tile);
 /* debug: in a library built with -DFLAIR_CONV_TRACE_BUILD and run with FLAIR_CONV_TRACE=1, CTA 0 of every conv
  * launch records clock64() at 15 points (see conv_igemm.cu); copies the 16 values of the most recent launch to
  * the host (synchronises).  All zeros in a normal build. */
