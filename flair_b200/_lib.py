@@ -118,6 +118,11 @@ def lib() -> C.CDLL:
         _lib.flair_scale_pixels.argtypes = [vp, vp, ll, i, i, i, vp]
         _lib.flair_flow_warp2.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]
         _lib.flair_deform_conv.argtypes = [C.POINTER(DeformConvParams), vp]
+        if hasattr(_lib, "flair_warp_affine_cubic_f32"):  # (absent from an older A/B library)
+            _lib.flair_warp_affine_cubic_f32.argtypes = [vp, vp, vp, i, i, i, i, i, i, C.POINTER(C.c_float), i, i, vp]
+            _lib.flair_parse_mask_f32.argtypes = [vp, vp, i, i, i, i, C.c_uint, vp]
+            _lib.flair_gaussian_blur_f32.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, f, vp]
+            _lib.flair_aux_blend_f32.argtypes = [vp, vp, vp, vp, C.c_double, i, i, i, i, i, vp]
     return _lib
 
 

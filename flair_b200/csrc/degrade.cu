@@ -24,6 +24,12 @@ constexpr int kTileH = 16, kTileW = 64, kOutPerThread = 4;
 // The in-map part of every row is read with 16-byte loads, four rows per warp in flight (a 16 x 64 LR tile of the
 // x4 blur needs 72 full 256-pixel rows: with one 4-byte load per lane and 4 in flight the CTA kept ~4 KB outstanding
 // and blur_down ran at 1.06 TB/s, profiles/r02_hbm_probe.txt); the replicated border columns are filled afterwards.
+//
+// SWZ: the 16-byte chunks of a row are stored XOR-swizzled (chunk q at q ^ ((q >> 3) & 7); pitch a multiple of 32
+// floats), see blur_down_tiled_kernel.
+__device__ __forceinline__ int swz_col(int c) { return (((c >> 2) ^ ((c >> 5) & 7)) << 2) | (c & 3); }
+
+template <bool SWZ = false>
 __device__ __forceinline__ void stage_tile(const float* __restrict__ xp, float* __restrict__ s_in, int i0, int j0,
                                            int span_h, int span_w, int pitch, int H, int W) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -47,8 +53,13 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ xp, float* 
       for (int q = 0; q < kRows; ++q) {
         const int ii = ii0 + q;
         if (ii < span_h) {
-          float* sp = s_in + ii * pitch + (ja4 - j0) + 4 * v;   // (not 16-byte aligned in general)
-          sp[0] = raw[q].x; sp[1] = raw[q].y; sp[2] = raw[q].z; sp[3] = raw[q].w;
+          float* sp = s_in + ii * pitch;
+          const int c = (ja4 - j0) + 4 * v;                      // (not 16-byte aligned in general)
+          if (SWZ) {
+            sp[swz_col(c)] = raw[q].x; sp[swz_col(c + 1)] = raw[q].y; sp[swz_col(c + 2)] = raw[q].z; sp[swz_col(c + 3)] = raw[q].w;
+          } else {
+            sp[c] = raw[q].x; sp[c + 1] = raw[q].y; sp[c + 2] = raw[q].z; sp[c + 3] = raw[q].w;
+          }
         }
       }
     }
@@ -59,37 +70,51 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ xp, float* 
   for (int idx = threadIdx.x; idx < span_h * rest; idx += blockDim.x) {
     const int ii = idx / rest, k = idx - ii * rest;
     const int jj = k < left ? k : right0 + (k - left);
-    s_in[ii * pitch + jj] = __ldg(xp + static_cast<long long>(clampi(i0 + ii, 0, H - 1)) * W + clampi(j0 + jj, 0, W - 1));
+    s_in[ii * pitch + (SWZ ? swz_col(jj) : jj)] =
+        __ldg(xp + static_cast<long long>(clampi(i0 + ii, 0, H - 1)) * W + clampi(j0 + jj, 0, W - 1));
   }
 }
+
+// Shared-memory layout: a thread's tap-row window is the 24 floats at column 16 * ln, so the lanes of a warp are 64 bytes
+// apart and every scalar load hit ONE bank pair 16 ways (39 us for 50 MB at 64 frames: the kernel was bound by
+// shared-memory wavefronts, not HBM).  The window is now read as six 16-byte loads from an XOR-swizzled row (chunk q
+// at q ^ ((q >> 3) & 7)): the eight lanes of a quarter warp hit eight different bank groups.
+constexpr int blur_down_pitch(int span_w) { return (((span_w + 3) / 4 + 7) & ~7) * 4; }
 
 template <int K, int SF>
 __global__ void __launch_bounds__(256)
 blur_down_tiled_kernel(const float* __restrict__ x, float* __restrict__ lr, const float* __restrict__ taps, int pre,
                        int H, int W) {
   pdl_sync();
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   constexpr int r = K / 2;
   constexpr int tile_w = 64, tile_h = 16;                       // LR outputs per CTA (16 threads x 4 per row)
   constexpr int span_h = tile_h * SF + K - 1, span_w = tile_w * SF + K - 1;
+  constexpr int pitch = blur_down_pitch(span_w);
   constexpr int win = K + (kOutPerThread - 1) * SF;             // HR inputs of one tap row for 4 adjacent outputs
+  constexpr int win4 = (win + 3) / 4;
+  static_assert(kOutPerThread * SF == 16 && (tile_w / kOutPerThread - 1) * 16 + win4 * 4 <= pitch, "window layout");
   const int h = H / SF, w = W / SF;
   float* s_taps = sm;
   float* s_in = sm + ((K * K + 3) & ~3);
   const int plane = blockIdx.z;
   const int m0 = blockIdx.y * tile_h, n0 = blockIdx.x * tile_w;
   for (int i = threadIdx.x; i < K * K; i += blockDim.x) s_taps[i] = __ldg(taps + i);
-  stage_tile(x + static_cast<long long>(plane) * H * W, s_in, m0 * SF + pre - r, n0 * SF + pre - r, span_h, span_w,
-             span_w, H, W);
+  stage_tile<true>(x + static_cast<long long>(plane) * H * W, s_in, m0 * SF + pre - r, n0 * SF + pre - r, span_h,
+                   span_w, pitch, H, W);
   __syncthreads();
   const int lm = threadIdx.x >> 4, ln = threadIdx.x & 15;
   float acc[kOutPerThread] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
   for (int u = 0; u < K; ++u) {
-    const float* row = s_in + (lm * SF + u) * span_w + ln * kOutPerThread * SF;
-    float wv[win];
+    const float4* row = reinterpret_cast<const float4*>(s_in + (lm * SF + u) * pitch);
+    float wv[win4 * 4];
 #pragma unroll
-    for (int j = 0; j < win; ++j) wv[j] = row[j];
+    for (int j = 0; j < win4; ++j) {
+      const int q = 4 * ln + j;
+      const float4 f = row[q ^ ((q >> 3) & 7)];
+      wv[4 * j] = f.x; wv[4 * j + 1] = f.y; wv[4 * j + 2] = f.z; wv[4 * j + 3] = f.w;
+    }
 #pragma unroll
     for (int v = 0; v < K; ++v) {
       const float t = s_taps[u * K + v];
@@ -432,7 +457,7 @@ extern "C" int flair_blur_down_f32(const float* x, float* lr, const float* taps,
   FLAIR_REQUIRE(k > 0 && (k & 1) && sf > 0 && H % sf == 0 && W % sf == 0 && pre >= 0 && pre < sf,
                 "flair_blur_down_f32: bad geometry k=%d sf=%d pre=%d H=%d W=%d", k, sf, pre, H, W);
   if (k == 9 && sf == 4) {  // the FLAIR blur operator (pseudoSR.py: 9 x 9 ds_kernel, factor 4)
-    const size_t smem = sizeof(float) * (84 + static_cast<size_t>(16 * 4 + 8) * (64 * 4 + 8));
+    const size_t smem = sizeof(float) * (84 + static_cast<size_t>(16 * 4 + 8) * blur_down_pitch(64 * 4 + 8));
     static FlairPerDeviceOnce attr;
     if (attr.first())
       FLAIR_CHECK_CUDA(cudaFuncSetAttribute(blur_down_tiled_kernel<9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -69,18 +69,20 @@ __device__ __forceinline__ float up_at(const UpdArgs& a, const float* q, int i, 
   return acc;
 }
 
-// Up(q) for the FLAIR blur operator (scale factor 4, 9 x 9 taps, 0 <= pre < 4) for the FOUR adjacent outputs
+// Up(q) for the FLAIR blur operator (scale factor 4, 9 x 9 taps, 0 <= PRE < 4) for the FOUR adjacent outputs
 // (i, j..j+3), j % 4 == 0, of one thread.  Same taps in the same (u, v) order as up_at (skipped taps enter as exact
-// zeros), but: the <= 3 x 3 contributing taps of every polyphase (u0, v0) come from a phase-major table in shared
-// memory (s_tp[u0][v0][3][3], zero where u or v >= 9), and the four outputs share ONE 3 x 4 patch of q held in
-// registers (12 loads per thread instead of 36 predicated ones; the per-output version ran the fused update at
-// 1.9 TB/s, issue-bound: profiles/r02_hbm_probe.txt).
+// zeros), but: the four outputs share ONE 3 x 4 patch of q held in registers (12 loads per thread instead of 36
+// predicated ones), and the <= 3 x 3 contributing taps of the four column phases come as one 16-byte shared load per
+// (uu, vv) from a phase-major table s_tp[u0][uu][vv][k] = taps[u0 + 4 uu][v0(k) + 4 vv] (zero outside the 9 x 9
+// support), v0(k) = (PRE - k) & 3.  PRE is a template parameter so that the patch column of every tap is a
+// compile-time register index.  (The per-output version ran the fused update at 1.9 TB/s, issue-bound.)
+template <int PRE>
 __device__ __forceinline__ void up4_sf4k9(const UpdArgs& a, const float* __restrict__ s_tp, const float* __restrict__ q,
                                           int i, int j, float (&out)[4]) {
   const int h = a.H >> 2, w = a.W >> 2;
-  const int u0 = (a.pre + 4 - i) & 3;
-  const int mb = (i + u0 - 4 - a.pre) >> 2;  // LR row of tap row u0 (exact: the numerator is a multiple of 4)
-  const int nb = (j >> 2) - 1;               // LR column of the left-most contributing tap of output j
+  const int u0 = (PRE + 4 - i) & 3;
+  const int mb = (i + u0 - 4 - PRE) >> 2;  // LR row of tap row u0 (exact: the numerator is a multiple of 4)
+  const int nb = (j >> 2) - 1;             // LR column of the left-most contributing tap of output j
   float Q[3][4];
 #pragma unroll
   for (int uu = 0; uu < 3; ++uu) {
@@ -92,30 +94,35 @@ __device__ __forceinline__ void up4_sf4k9(const UpdArgs& a, const float* __restr
       Q[uu][cc] = (row_ok && n >= 0 && n < w) ? __ldg(q + m * w + n) : 0.0f;
     }
   }
+  const float4* tp = reinterpret_cast<const float4*>(s_tp) + u0 * 9;
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int v0 = (a.pre - k) & 3;
-    const bool off = ((k + v0 - a.pre) >> 2) != 0;  // first contributing LR column: nb (+1)
-    const float* tp = s_tp + (u0 * 4 + v0) * 9;
-    float acc = 0.0f;
+  for (int uu = 0; uu < 3; ++uu) {
 #pragma unroll
-    for (int uu = 0; uu < 3; ++uu) {
+    for (int vv = 0; vv < 3; ++vv) {
+      const float4 t = tp[uu * 3 + vv];
+      const float tk[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-      for (int vv = 0; vv < 3; ++vv) acc = fmaf(tp[uu * 3 + vv], off ? Q[uu][vv + 1] : Q[uu][vv], acc);
+      for (int k = 0; k < 4; ++k) {
+        const int v0 = (PRE - k) & 3;
+        const int off = (k + v0 - PRE) >> 2;   // first contributing LR column of output k: nb (+1); compile-time
+        acc[k] = fmaf(tk[k], Q[uu][vv + off], acc[k]);
+      }
     }
-    out[k] = acc;
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) out[k] = acc[k];
 }
 
 __global__ void __launch_bounds__(256) sampler_update_kernel(const __grid_constant__ UpdArgs a) {
   pdl_sync();  // PDL: release the next launch, then wait for the previous kernel's results
-  __shared__ float s_tp[144];  // [u0][v0][uu][vv] = taps[u0 + 4 uu][v0 + 4 vv] (0 outside the 9 x 9 support)
+  __shared__ __align__(16) float s_tp[144];  // [u0][uu][vv][k] = taps[u0 + 4 uu][v0(k) + 4 vv] (0 outside the support)
   const bool fast_up = a.q_lr != nullptr && a.sf == 4 && a.kk == 9 && a.pre >= 0 && a.pre < 4 && (a.W & 3) == 0 &&
                        (a.H & 3) == 0;
   if (fast_up) {
     if (threadIdx.x < 144) {
-      const int ph = threadIdx.x / 9, r = threadIdx.x - ph * 9;
-      const int u = (ph >> 2) + 4 * (r / 3), v = (ph & 3) + 4 * (r % 3);
+      const int k = threadIdx.x & 3, r = (threadIdx.x >> 2) % 9, pu = threadIdx.x / 36;
+      const int u = pu + 4 * (r / 3), v = ((a.pre - k) & 3) + 4 * (r % 3);
       s_tp[threadIdx.x] = (u < 9 && v < 9) ? __ldg(a.up_taps + u * 9 + v) : 0.0f;
     }
     __syncthreads();
@@ -158,7 +165,12 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(const __grid_consta
       const float* q = a.q_lr + plane * (hw / (a.sf * a.sf));
       if (fast_up) {
         float up[4];
-        up4_sf4k9(a, s_tp, q, i, j, up);
+        switch (a.pre) {
+          case 0: up4_sf4k9<0>(a, s_tp, q, i, j, up); break;
+          case 1: up4_sf4k9<1>(a, s_tp, q, i, j, up); break;
+          case 2: up4_sf4k9<2>(a, s_tp, q, i, j, up); break;
+          default: up4_sf4k9<3>(a, s_tp, q, i, j, up); break;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) x0[k] = clampf(__fsub_rn(x0[k], __fmul_rn(gamma, up[k])), a.clip);
       } else {

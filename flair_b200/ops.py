@@ -555,3 +555,56 @@ def scale_pixels_(x, wmap):
     N, H, W, Cc = x.shape
     L.check(L.lib().flair_scale_pixels(_ptr(x), _ptr(wmap), N * H * W, Cc, _cs4(x), _DT[x.dtype], _stream()))
     return x
+
+
+# ---------------------------------------------------------------------------------------------------------
+# aux face-prior warps: facelib/utils/face_restoration_helper.py:225-345 on the device
+# ---------------------------------------------------------------------------------------------------------
+def warp_affine_cubic(src, minv, out_hw, *, border=None, in_mode=0, out_mode=0):
+    """src (N, C<=4, Hs, Ws) fp32 -> (N, C, Hd, Wd); `minv` (N, 6) float64 DEVICE tensor = destination->source maps.
+    cv2.warpAffine(INTER_CUBIC, BORDER_CONSTANT) arithmetic; in_mode/out_mode 1 fuse the [-1,1] <-> [0,255] maps."""
+    src = _f32c(src)
+    N, Cc, Hs, Ws = src.shape
+    assert minv.is_cuda and minv.dtype == torch.float64 and minv.is_contiguous() and minv.numel() == 6 * N
+    Hd, Wd = out_hw
+    dst = torch.empty(N, Cc, Hd, Wd, dtype=torch.float32, device=src.device)
+    b = None
+    if border is not None:
+        assert len(border) == Cc
+        b = (C.c_float * Cc)(*[float(v) for v in border])
+    L.check(L.lib().flair_warp_affine_cubic_f32(_ptr(src), _ptr(dst), _ptr(minv), N, Cc, Hs, Ws, Hd, Wd, b,
+                                                int(in_mode), int(out_mode), _stream()))
+    return dst
+
+
+def parse_mask(logits, lut_bits):
+    """(N, classes, H, W) fp32 logits -> (N, 1, H, W) fp32 mask: 255 where bit argmax of `lut_bits` is set, else 0."""
+    logits = _f32c(logits)
+    N, K, H, W = logits.shape
+    mask = torch.empty(N, 1, H, W, dtype=torch.float32, device=logits.device)
+    L.check(L.lib().flair_parse_mask_f32(_ptr(logits), _ptr(mask), N, K, H, W, int(lut_bits), _stream()))
+    return mask
+
+
+def gaussian_blur101(x, taps, *, finish=False, thres=10, scale=255.0, out=None, tmp=None):
+    """cv2.GaussianBlur(x, (101, 101), sigma) per (N, 1, H, W) plane; taps = fp32 cast of getGaussianKernel(101, sigma)
+    on the device.  finish: clear a `thres` frame and divide by `scale` (inverse_faces :309-318)."""
+    x = _f32c(x)
+    N, H, W = x.shape[0] * x.shape[1], x.shape[2], x.shape[3]
+    out = torch.empty_like(x) if out is None else out
+    tmp = torch.empty_like(x) if tmp is None else tmp
+    assert taps.is_cuda and taps.dtype == torch.float32 and taps.numel() == 101
+    L.check(L.lib().flair_gaussian_blur_f32(_ptr(x), _ptr(out), _ptr(tmp), _ptr(taps), 101, N, H, W, int(finish),
+                                            int(thres), float(scale), _stream()))
+    return out
+
+
+def aux_blend(x0, face, mask, w, *, clip_denoised=True):
+    """w x0 + (1 - w) clamp(x0 (1 - mask) + face mask)   (gaussian_diffusion.py:488-496); mask (N, 1, H, W)."""
+    x0, face, mask = _f32c(x0), _f32c(face), _f32c(mask)
+    N, Cc, H, W = x0.shape
+    assert face.shape == x0.shape and mask.shape == (N, 1, H, W)
+    out = torch.empty_like(x0)
+    L.check(L.lib().flair_aux_blend_f32(_ptr(x0), _ptr(face), _ptr(mask), _ptr(out), float(w), N, Cc, H, W,
+                                        int(clip_denoised), _stream()))
+    return out

@@ -126,8 +126,13 @@ def rnn_frames(task, lr_pm1, size):
 
 @torch.no_grad()
 def restore_window(model, diffusion, A, task, lr01, *, image_size, prev_recon=None, knobs=None, t_start=-1,
-                   noise_tape=None, generator=None, vsrpp_weights=1.0):
-    """One window: lr01 (T,3,h,w) in [0,1] on the device -> restored (T,3,S,S) in [-1,1] (fp32, device)."""
+                   noise_tape=None, generator=None, vsrpp_weights=1.0, aux=None):
+    """One window: lr01 (T,3,h,w) in [0,1] on the device -> restored (T,3,S,S) in [-1,1] (fp32, device).
+
+    aux: None, or the aux face prior of the reference script (scripts/video_sample.py:446-475) as a dict
+    {aux_model, face_restore_helper, affine_matrices, w, tau, aligned}: `aux_model` is the reference's PyTorch prior
+    (CodeFormer), `face_restore_helper` a guided_diffusion.facelib FaceRestoreHelper (device-side crops / inverse
+    warps), `affine_matrices` one 2x3 matrix per frame of the window."""
     knobs = knobs or KNOBS[task]
     T = lr01.shape[0]
     dev = lr01.device
@@ -148,8 +153,9 @@ def restore_window(model, diffusion, A, task, lr01, *, image_size, prev_recon=No
     final = None
     for out in diffusion.p_sample_loop_progressive(
             model, noise.shape, noise=noise, model_kwargs=model_kwargs, device=dev, restore_fn=restore,
-            aux_model=None, rho=knobs.rho, noise_level=knobs.noise_level, zeta=knobs.zeta, prev_recon=prev_recon,
-            t_start=t_start, noise_tape=tape, generator=generator, _views=True):
+            rho=knobs.rho, noise_level=knobs.noise_level, zeta=knobs.zeta, prev_recon=prev_recon,
+            t_start=t_start, noise_tape=tape, generator=generator, _views=True,
+            **({"aux_model": None} if aux is None else aux)):
         final = out
     return final["sample"].clone()  # the graphed step yields its static buffers: detach the result from them
 

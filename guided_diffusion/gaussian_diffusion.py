@@ -307,18 +307,25 @@ class GaussianDiffusion:
         aux_face = aux_model(aux_face, t, aux_xt)
         if not aligned:
             inv_face, inv_mask = face_restore_helper.inverse_faces(aux_face, affine_matrices)
-            x_with_face = x0 * (1 - inv_mask) + inv_face * inv_mask
-        else:
-            x_with_face = aux_face
-        if clip_denoised:
-            x_with_face = x_with_face.clamp(-1, 1)
-        x0 = w * x0 + (1 - w) * x_with_face
+        else:  # x_with_face = aux_face: the blend with a mask of ones (x0 * 0 + face * 1 is exact)
+            inv_face = aux_face
+            inv_mask = self._ones_mask(x0)
+        # x_with_face = x0 (1 - m) + face m; clamp; x0 <- w x0 + (1 - w) x_with_face  (:488-496), one launch
+        x0 = ops.aux_blend(x0, inv_face, inv_mask, float(w), clip_denoised=clip_denoised)
         if prev is not None:
             x0 = x0.reshape(-1, frames, *x0.shape[1:]).clone()
             x0[:, : prev.shape[1]].copy_(prev)
             x0 = x0.reshape(-1, *x0.shape[2:])
         sample, x0 = ops.sampler_update(x, coef, x0_in=x0, noise=noise, t_arr=t64, rho=rho)
         return {"sample": sample, "pred_xstart": x0}
+
+    def _ones_mask(self, x0):
+        key = (x0.device, x0.shape[0], x0.shape[2], x0.shape[3])
+        cache = self.__dict__.setdefault("_ones_masks", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = th.ones(x0.shape[0], 1, x0.shape[2], x0.shape[3], device=x0.device)
+        return cache[key]
 
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, model_kwargs=None, device=None,
                       progress=False, affine_matrices=None, restore_fn=None, face_restore_helper=None,

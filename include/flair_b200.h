@@ -376,6 +376,32 @@ typedef struct flair_deform_conv_params {
 
 int flair_deform_conv(const flair_deform_conv_params* p, void* stream);
 
+/* ----------------------------------------------------------------------
+ * Aux face-prior warps, fp32 NCHW planes.  Replace the OpenCV CPU round trips of
+ * guided_diffusion/facelib/utils/face_restoration_helper.py:225-253 (get_crop_face_from_affine_matrices),
+ * :264-345 (inverse_faces) and the blend of gaussian_diffusion.py:488-496.  Arithmetic = OpenCV's float path
+ * (1/32-pixel fixed-point source positions, 32-entry bicubic table with A = -0.75, constant border).
+ * ---------------------------------------------------------------------- */
+/* dst[n,c] = cv2.warpAffine(src[n,c], M_n, (Wd, Hd), INTER_CUBIC, BORDER_CONSTANT, border[c]).
+ * minv: [N][6] doubles on the DEVICE = destination->source map (M_n inverted as cv2.warpAffine /
+ * cv2.invertAffineTransform do, in double, on the host).  border: [C] host floats or NULL (0).
+ * in_mode 1: src holds [-1,1] images, sampled as clamp((x+1)/2,0,1)*255 (:229);  out_mode 1: result stored as
+ * clamp((v/255-0.5)/0.5,-1,1) (:246-252).  C <= 4. */
+int flair_warp_affine_cubic_f32(const float* src, float* dst, const double* minv, int N, int C, int Hs, int Ws,
+                                int Hd, int Wd, const float* border, int in_mode, int out_mode, void* stream);
+/* mask[n,y,x] = 255 if bit argmax_c(logits[n,c,y,x]) of lut_bits is set else 0 (:265-306: face_parse(...)[0].argmax(1)
+ * + MASK_COLORMAP; first maximum wins like torch.argmax).  classes <= 32. */
+int flair_parse_mask_f32(const float* logits, float* mask, int N, int classes, int H, int W, unsigned int lut_bits,
+                         void* stream);
+/* out = cv2.GaussianBlur(in, (101, 101), sigma) per image (separable, BORDER_REFLECT_101; taps = the 101 fp32 casts of
+ * cv2.getGaussianKernel(101, sigma)).  tmp: N*H*W floats.  finish != 0: additionally clear a `thres`-pixel frame and
+ * divide by `scale` (:309-318).  out may alias in. */
+int flair_gaussian_blur_f32(const float* in, float* out, float* tmp, const float* taps, int ksize, int N, int H, int W,
+                            int finish, int thres, float scale, void* stream);
+/* out = w x0 + (1-w) clamp(x0 (1-mask) + face mask)  — gaussian_diffusion.py:488-496.  mask: (N,1,H,W). */
+int flair_aux_blend_f32(const float* x0, const float* face, const float* mask, float* out, double w, int N, int C,
+                        int H, int W, int clip, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

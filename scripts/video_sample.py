@@ -6,9 +6,9 @@ INIT_FUNC / CKPT_PATH / RESTORE_FUNC, FRAME_SLICE_LEN, OVERLAP).
 Differences that are deliberate:
   * the windowing / sampling loop lives in flair_b200.pipeline (shared with bench.py);
   * `image_size` is a parameter (the reference hard-wires 512);
-  * the auxiliary CodeFormer face prior and facelib are out of scope (BASELINE.json north_star): when
-    their checkpoints / packages are absent the sampler runs with `aux_model=None`, which is the
-    reference's behaviour for w = 1;
+  * the auxiliary CodeFormer face prior and the facelib networks are out of scope (BASELINE.json north_star):
+    this script samples with `aux_model=None` (the reference's behaviour for w = 1); the per-step crops / inverse
+    warps of the prior are device kernels (guided_diffusion/facelib) usable through flair_b200.pipeline;
   * cyclopts is optional (argparse fallback with the same sub-command spellings).
 """
 from __future__ import annotations
@@ -121,11 +121,13 @@ def main(task, video_path, output_path, device=torch.device("cuda"), t_start=-1,
     else:
         # checkpoints are plain state dicts: refuse arbitrary pickles
         model.load_state_dict(torch.load(CKPT_PATH[task], map_location="cpu", weights_only=True))
-    # The auxiliary face prior (CodeFormer + facelib crops, reference :350-360,446-456) is reference PyTorch outside
-    # this repo's scope (BASELINE.json north_star); this script always samples with aux_model=None, so `w`, `tau`
-    # and `aligned` have no effect here.  guided_diffusion.gaussian_diffusion.p_sample keeps the reference's
-    # aux-prior branch (tests/test_gpu_round2.py::test_p_sample_aux_branch_vs_oracle): pass `aux_model=` to
-    # SpacedDiffusion.sample() to use a prior of your own.
+    # The auxiliary face prior (reference :350-360,446-456): the CodeFormer network, RetinaFace detection and ParseNet
+    # are reference PyTorch modules outside this repo (BASELINE.json north_star) and their checkpoints cannot be
+    # fetched here, so this script samples with aux_model=None and `w`, `tau`, `aligned` have no effect.  The per-step
+    # part of the prior IS implemented on the device: guided_diffusion.facelib FaceRestoreHelper (affine crops,
+    # inverse warps, parsing mask; tests/test_gpu_aux.py) and the aux branch of p_sample — hand your modules to
+    # flair_b200.pipeline.restore_window(..., aux=dict(aux_model=..., face_restore_helper=FaceRestoreHelper(
+    # face_parse=...), affine_matrices=..., w=w, tau=tau, aligned=aligned)).
     print("auxiliary face prior (CodeFormer) is not part of this build: sampling with aux_model=None "
           f"(w={w}, tau={tau}, aligned={aligned} are ignored)")
     if task in ("x8_bicubic", "x16_bicubic"):
