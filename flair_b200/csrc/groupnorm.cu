@@ -97,25 +97,35 @@ gn_stats_kernel(const void* __restrict__ x, int dtype, long long P, int C, int c
   // the accumulation order per thread is unchanged, so the statistics are bit-identical to the simple loop
   // (ncu: with 2 resident CTAs x 8 loads DRAM was 23 % busy and nothing else above 16 %: latency-bound.  The loads
   // are kept as raw 16-byte registers until consumed so that 4 CTAs fit per SM: 32 warps x 8 x 512 B in flight.)
-  constexpr int kU = 8;
+  // Round 2: the batches are software-pipelined — the loads of batch i+1 are issued BEFORE batch i is accumulated, so a
+  // warp always has 4-8 loads outstanding instead of alternating "8 in flight" / "none in flight" (a CTA walks ~9
+  // dependent batches: that serialisation, not the byte count, set the 4.6 TB/s streaming rate).
+  constexpr int kU = 4;
   long long p = p0 + pl;
   if (dtype != FLAIR_F32) {
     const uint16_t* xp = static_cast<const uint16_t*>(x);
-    for (; p < p1; p += static_cast<long long>(kU) * ppb) {  // predicated batches, same accumulation order
-      uint4 raw[kU];
+    const long long step = static_cast<long long>(kU) * ppb;
+    uint4 cur[kU], nxt[kU];
+    auto load = [&](uint4 (&r)[kU], long long pp) {
 #pragma unroll
       for (int u = 0; u < kU; ++u)
-        if (p + static_cast<long long>(u) * ppb < p1)
-          raw[u] = __ldg(reinterpret_cast<const uint4*>(xp + (base + p + static_cast<long long>(u) * ppb) * cstride + cv * 8));
+        if (pp + static_cast<long long>(u) * ppb < p1)
+          r[u] = __ldg(reinterpret_cast<const uint4*>(xp + (base + pp + static_cast<long long>(u) * ppb) * cstride + cv * 8));
+    };
+    load(cur, p);
+    for (; p < p1; p += step) {  // predicated batches, same accumulation order as the simple loop
+      load(nxt, p + step);
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         if (p + static_cast<long long>(u) * ppb < p1) {
           float v[8];
-          unpack8(raw[u], dtype, v);
+          unpack8(cur[u], dtype, v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
         }
       }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) cur[u] = nxt[u];
     }
   }
   for (; p < p1; p += ppb) {
@@ -473,24 +483,33 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fast_kernel(const __grid_cons
       v[j] = y;
     }
   };
-  constexpr int kU = 8;  // independent 16-byte loads in flight per thread, kept raw until consumed (register budget)
+  // 16-byte loads kept raw until consumed (register budget); software-pipelined like gn_stats: the loads of batch i+1
+  // are in flight while batch i is transformed and stored
+  constexpr int kU = 4;
   long long p = static_cast<long long>(blockIdx.x) * ppb + pl;
   if (a.in_dtype != FLAIR_F32) {
     const uint16_t* xp = static_cast<const uint16_t*>(a.x);
-    for (; p < P; p += kU * stride) {  // predicated batches: no scalar tail (it ran with one load in flight)
-      uint4 raw[kU];
+    const long long step = kU * stride;
+    uint4 cur[kU], nxt[kU];
+    auto load = [&](uint4 (&r)[kU], long long pp) {
 #pragma unroll
       for (int u = 0; u < kU; ++u)
-        if (p + u * stride < P) raw[u] = __ldg(reinterpret_cast<const uint4*>(xp + (base + p + u * stride) * a.x_cstride + c0));
+        if (pp + u * stride < P) r[u] = __ldg(reinterpret_cast<const uint4*>(xp + (base + pp + u * stride) * a.x_cstride + c0));
+    };
+    load(cur, p);
+    for (; p < P; p += step) {  // predicated batches: no scalar tail (it ran with one load in flight)
+      load(nxt, p + step);
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         if (p + u * stride < P) {
           float v[8];
-          unpack8(raw[u], a.in_dtype, v);
+          unpack8(cur[u], a.in_dtype, v);
           xform(v);
           store8(a.out, (base + p + u * stride) * a.out_cstride + c0, a.out_dtype, v);
         }
       }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) cur[u] = nxt[u];
     }
   }
   for (; p < P; p += stride) {
@@ -629,7 +648,9 @@ extern "C" int flair_gn_apply(const flair_gn_apply_params* p, void* stream_) {
     const int ppb = 256 / vecs_;
     const int frames = p->B * p->T;
     long long bx = ceil_div_ll(P, static_cast<long long>(ppb) * 16);  // >= 16 pixels per thread (prologue amortised)
-    const long long cap = ceil_div_ll(static_cast<long long>(flair_num_sms()) * 3, frames);  // one wave of 3 CTAs per SM
+    // ONE wave of 3 CTAs per SM: rounded DOWN (rounding up gave 450 CTAs for 444 slots at 10 frames: six CTAs ran
+    // alone after the wave)
+    long long cap = static_cast<long long>(flair_num_sms()) * 3 / frames;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     FLAIR_CHECK_CUDA(flair_launch(gn_apply_fast_kernel, dim3(static_cast<unsigned>(bx), frames), dim3(256), 0, stream, a));
