@@ -402,9 +402,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ A
 // keeps one 8-channel vector, so the whole per-channel affine (statistics, gamma/beta, FiLM) folds into
 // y = x * A + B held in registers; the inner loop is one 16-byte load, 8 FMAs (+ SiLU), one 16-byte store.
 // grid (blocks, B*T)
-__global__ void __launch_bounds__(256, 3) gn_apply_fast_kernel(const __grid_constant__ ApplyArgs a) {
-  pdl_sync();
-  __shared__ float s_mean[kGroupsMax], s_rstd[kGroupsMax];
+// Prologue shared by the fast apply kernels: statistics of this frame's batch element into shared memory, then the
+// per-thread folded affine of the thread's 8 channels: y = x * A + B (statistics, gamma / beta, FiLM).
+__device__ __forceinline__ void gn_fold_affine(const ApplyArgs& a, float* s_mean, float* s_rstd, int& c0_out, int& pl_out,
+                                               int& ppb_out, float (&A)[8], float (&Bc)[8]) {
   const int frame = blockIdx.y;  // b*T + t
   const int b = frame / a.T;
   const int cpg = a.C / a.groups;
@@ -429,7 +430,6 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fast_kernel(const __grid_cons
   const int vecs = a.C / 8;
   const int cv = threadIdx.x % vecs, pl = threadIdx.x / vecs, ppb = blockDim.x / vecs;
   const int c0 = cv * 8;
-  float A[8], Bc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { A[j] = 1.0f; Bc[j] = 0.0f; }
   if (a.norm) {
@@ -467,6 +467,16 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fast_kernel(const __grid_cons
       }
     }
   }
+  c0_out = c0; pl_out = pl; ppb_out = ppb;
+}
+
+__global__ void __launch_bounds__(256, 3) gn_apply_fast_kernel(const __grid_constant__ ApplyArgs a) {
+  pdl_sync();
+  __shared__ float s_mean[kGroupsMax], s_rstd[kGroupsMax];
+  const int frame = blockIdx.y;  // b*T + t
+  int c0, pl, ppb;
+  float A[8], Bc[8];
+  gn_fold_affine(a, s_mean, s_rstd, c0, pl, ppb, A, Bc);
   const long long P = static_cast<long long>(a.H) * a.W;
   const long long base = static_cast<long long>(frame) * P;
   const long long stride = static_cast<long long>(gridDim.x) * ppb;
@@ -517,6 +527,99 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fast_kernel(const __grid_cons
     load8(a.x, (base + p) * a.x_cstride + c0, a.in_dtype, v);
     xform(v);
     store8(a.out, (base + p) * a.out_cstride + c0, a.out_dtype, v);
+  }
+}
+
+// Resampling variants of the fast path (ResBlock up / down, unet_new.py:249-254; sr3 Upsample): same per-thread folded
+// affine, 32-bit pixel arithmetic, several independent 16-byte loads in flight.  RS = 1: nearest x2 up (one input pixel
+// -> four stores), RS = 2: 2x2 average down (four transformed inputs -> one store, summed in (dy, dx) order like the
+// generic kernel).  grid (blocks, B*T).
+template <int RS>
+__global__ void __launch_bounds__(256, 3) gn_apply_rs_kernel(const __grid_constant__ ApplyArgs a) {
+  pdl_sync();
+  __shared__ float s_mean[kGroupsMax], s_rstd[kGroupsMax];
+  const int frame = blockIdx.y;
+  int c0, pl, ppb;
+  float A[8], Bc[8];
+  gn_fold_affine(a, s_mean, s_rstd, c0, pl, ppb, A, Bc);
+  auto xform = [&](float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = fmaf(v[j], A[j], Bc[j]);
+      if (a.silu) {
+        const float h = 0.5f * y;
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+        y = fmaf(h, t, h);
+      }
+      v[j] = y;
+    }
+  };
+  const int stride = gridDim.x * ppb;
+  const long long in_base = static_cast<long long>(frame) * a.H * a.W;
+  const uint16_t* xp = static_cast<const uint16_t*>(a.x);
+  if (RS == 1) {
+    const int P = a.H * a.W, Wo = 2 * a.W;
+    const long long out_base = in_base * 4;
+    constexpr int kU = 4;
+    for (int p = blockIdx.x * ppb + pl; p < P; p += kU * stride) {
+      uint4 raw[kU];   // 16-bit inputs only (host-checked): kept raw until consumed
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (p + u * stride < P) raw[u] = __ldg(reinterpret_cast<const uint4*>(xp + (in_base + p + u * stride) * a.x_cstride + c0));
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int pp = p + u * stride;
+        if (pp < P) {
+          float vv[8];
+          unpack8(raw[u], a.in_dtype, vv);
+          xform(vv);
+          const int h = pp / a.W, w = pp - h * a.W;
+          const long long o = out_base + static_cast<long long>(2 * h) * Wo + 2 * w;
+          store8(a.out, o * a.out_cstride + c0, a.out_dtype, vv);
+          store8(a.out, (o + 1) * a.out_cstride + c0, a.out_dtype, vv);
+          store8(a.out, (o + Wo) * a.out_cstride + c0, a.out_dtype, vv);
+          store8(a.out, (o + Wo + 1) * a.out_cstride + c0, a.out_dtype, vv);
+        }
+      }
+    }
+  } else {
+    const int Hi = a.H / 2, Wi = a.W / 2, Po = Hi * Wi;
+    const long long out_base = static_cast<long long>(frame) * Po;
+    constexpr int kU = 2;
+    for (int p = blockIdx.x * ppb + pl; p < Po; p += kU * stride) {
+      uint4 raw[kU][4];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int pp = p + u * stride;
+        if (pp < Po) {
+          const int h = pp / Wi, w = pp - h * Wi;
+          const long long i0 = in_base + static_cast<long long>(2 * h) * a.W + 2 * w;
+          raw[u][0] = __ldg(reinterpret_cast<const uint4*>(xp + i0 * a.x_cstride + c0));
+          raw[u][1] = __ldg(reinterpret_cast<const uint4*>(xp + (i0 + 1) * a.x_cstride + c0));
+          raw[u][2] = __ldg(reinterpret_cast<const uint4*>(xp + (i0 + a.W) * a.x_cstride + c0));
+          raw[u][3] = __ldg(reinterpret_cast<const uint4*>(xp + (i0 + a.W + 1) * a.x_cstride + c0));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int pp = p + u * stride;
+        if (pp < Po) {
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float vv[8];
+            unpack8(raw[u][q], a.in_dtype, vv);
+            xform(vv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += vv[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+          store8(a.out, (out_base + pp) * a.out_cstride + c0, a.out_dtype, acc);
+        }
+      }
+    }
   }
 }
 
@@ -643,6 +746,23 @@ extern "C" int flair_gn_apply(const flair_gn_apply_params* p, void* stream_) {
   a.x_cstride = p->x_cstride; a.out_cstride = p->out_cstride;
   a.norm = p->norm; a.silu = p->silu; a.resample = p->resample; a.eps = p->eps > 0 ? p->eps : 1e-5f;
   const int vecs_ = p->C / 8;
+  if (p->resample != 0 && p->in_dtype != FLAIR_F32 && vecs_ <= 256 && 256 % vecs_ == 0 &&
+      static_cast<long long>(p->B) * p->T < 65536 &&
+      static_cast<long long>(p->H) * p->W < (1ll << 30)) {
+    const int frames = p->B * p->T;
+    const int ppb = 256 / vecs_;
+    const long long items = (p->resample == 2) ? static_cast<long long>(p->H / 2) * (p->W / 2) : static_cast<long long>(p->H) * p->W;
+    long long bx = ceil_div_ll(items, static_cast<long long>(ppb) * 8);
+    long long cap = static_cast<long long>(flair_num_sms()) * 3 / frames;   // one wave of 3 CTAs per SM
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    if (p->resample == 1)
+      FLAIR_CHECK_CUDA(flair_launch(gn_apply_rs_kernel<1>, dim3(static_cast<unsigned>(bx), frames), dim3(256), 0, stream, a));
+    else
+      FLAIR_CHECK_CUDA(flair_launch(gn_apply_rs_kernel<2>, dim3(static_cast<unsigned>(bx), frames), dim3(256), 0, stream, a));
+    FLAIR_CHECK_LAUNCH();
+    return 0;
+  }
   if (p->resample == 0 && vecs_ <= 256 && 256 % vecs_ == 0 && static_cast<long long>(p->B) * p->T < 65536) {
     const long long P = static_cast<long long>(p->H) * p->W;
     const int ppb = 256 / vecs_;

@@ -145,6 +145,34 @@ def test_group_norm_film_silu(dev, C, groups, T, H, dt):
     assert _rel(y2, K.group_norm_cl(x, gamma, beta, groups)) < 1e-5
 
 
+@pytest.mark.parametrize("C,groups,T,H,dt,rs", [(64, 32, 3, 32, torch.float16, 1), (64, 32, 3, 32, torch.float16, 2),
+                                                 (256, 32, 2, 8, torch.bfloat16, 1), (128, 32, 2, 16, torch.float16, 2),
+                                                 (192, 32, 2, 16, torch.float16, 2)])
+def test_group_norm_resample(dev, C, groups, T, H, dt, rs):
+    """GroupNorm + FiLM + SiLU followed by the ResBlock's nearest x2 upsample / 2x2 average pool (unet_new.py:249-254),
+    and the plain resample of the skip path (no norm), in one launch each."""
+    import torch.nn.functional as F
+    from flair_b200 import ops
+    from oracle import kernels as K
+    g = torch.Generator().manual_seed(C + rs)
+    x = (torch.randn(2, T, H, H, C, generator=g) * 1.3 - 0.2).to(dt)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    film = torch.randn(2 * T, 2 * C, generator=g) * 0.2
+    xd, fd = x.to(dev), film.to(dev)
+
+    def resample(t):   # (B, T, H, W, C) fp32
+        n = t.reshape(-1, H, H, C).permute(0, 3, 1, 2)
+        n = F.interpolate(n, scale_factor=2, mode="nearest") if rs == 1 else F.avg_pool2d(n, 2)
+        return n.permute(0, 2, 3, 1).reshape(2, T, n.shape[2], n.shape[3], C)
+
+    y = ops.gn_apply(xd, ops.gn_stats(xd, groups), gamma.to(dev), beta.to(dev), scale=fd[:, :C], shift=fd[:, C:],
+                     silu=True, groups=groups, resample=rs)
+    ref = resample(K.group_norm_cl(x, gamma, beta, groups, scale=film[:, :C], shift=film[:, C:], silu=True).float())
+    assert y.shape == ref.shape and _rel(y, ref) < _tol(dt)
+    y2 = ops.gn_apply(xd, None, resample=rs)
+    assert _rel(y2, resample(x.float())) < (1e-6 if rs == 1 else _tol(dt))
+
+
 @pytest.mark.parametrize("heads,L", [(4, 16), (8, 8), (8, 4)])
 def test_spatial_attention(dev, heads, L):
     from flair_b200 import ops
