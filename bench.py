@@ -317,6 +317,7 @@ def run_sharded(job, steps, warmup, world, rank, barrier, reduce_max):
 def run_native(args):
     import torch.distributed as dist
     from flair_b200 import _lib as L
+    from flair_b200 import ops as _ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -412,6 +413,7 @@ def run_native(args):
                        "l2": "inputs larger than L2: activations of one forward (2.9 GB) exceed the 126 MB L2",
                        "operands": "fp16 tcgen05 (fp32 accumulate), same tensor rate as bf16",
                        "step_graph": os.environ.get("FLAIR_STEP_GRAPH", "1") != "0",
+                       "fused_gn_statistics": bool(_ops.FUSED_GN),
                        "unet_fwd_tflops_algorithmic": fwd_tflops,
                        "unet_fwd_frac_of_peak": fwd_tflops / pk["tflops"] / world},
             "clocks": clocks.summary(),

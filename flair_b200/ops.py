@@ -321,7 +321,12 @@ def _gn_counter(device, B):
     return c
 
 
-FUSED_GN = os.environ.get("FLAIR_FUSED_GN", "1") != "0"   # A/B switch: 0 = always run the separate statistics kernel
+# GroupNorm statistics from the producing conv's epilogue (flair_conv_params.gn_partial + flair_gn_finalize) are
+# implemented and tested, but OFF by default: the warp-shuffle reduction in the epilogue shares the L1 data pipe with
+# the tensor core's shared-memory operand reads, the 152 batched convs that carry it get ~20 us slower each (conv
+# replay 32.7 -> 35.8 ms) and the forward is 56.2 ms with it against 55.4 ms with the separate (pipelined) statistics
+# kernel (ABBA on one box, profiles/r02_summary.md).  FLAIR_FUSED_GN=1 turns it on.
+FUSED_GN = os.environ.get("FLAIR_FUSED_GN", "0") == "1"
 
 
 def gn_stats(x, groups=32, eps=1e-5):

@@ -72,3 +72,20 @@ def test_video_mode_weight_map(model_and_fx):
     err = rel_err(out.cpu(), fx["video_out_weighted"])
     print("video-mode (weight map) rel L2", err)
     assert err < 4e-3
+
+
+def test_video_mode_fused_group_norm_statistics(model_and_fx, monkeypatch):
+    """The optional path where every conv that feeds a GroupNorm leaves the statistics from its own epilogue
+    (FLAIR_FUSED_GN=1; off by default, see flair_b200/ops.py): same forward, eager launches (the cached graph of the
+    fixture was captured without it)."""
+    from flair_b200 import ops
+    model, fx = model_and_fx
+    model.compute_dtype = model.stream_dtype = torch.float16
+    monkeypatch.setattr(ops, "FUSED_GN", True)
+    monkeypatch.setattr(model, "use_cuda_graph", False)
+    dev = "cuda"
+    out = model(fx["x"].to(dev), fx["video_t"].to(dev), low_res_input=fx["low_res"][None].to(dev), num_frames=4,
+                rnn_input=fx["rnn_input"][None].to(dev), enable_cross_frames=True, vsrpp_weights=1.0)
+    err = rel_err(out.cpu(), fx["video_out"])
+    print("video-mode rel L2 with fused GroupNorm statistics", err)
+    assert err < 4e-3
