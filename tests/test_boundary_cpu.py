@@ -233,3 +233,21 @@ def test_checkpoint_layout_after_convert_to_fp16(task, ref_task):
     k0 = next(k for k, (s, dt) in ref.items() if dt == "torch.float16")
     assert model.state_dict()[k0].dtype == torch.float16 and float(model.state_dict()[k0].flatten()[0]) == 0.5
     assert diffusion.num_timesteps == 100
+
+
+def test_script_reads_frames_in_natural_order(tmp_path):
+    """scripts/video_sample.py::_read_frames (reference :287-300: PNG/JPG frames of a folder in natural order, RGB,
+    [0, 1]) — the host side of the f1 caller path, no GPU needed."""
+    import cv2
+    import numpy as np
+    m = _script()
+    vals = {"2.png": 20, "10.png": 100, "1.png": 10}
+    for name, v in vals.items():
+        img = np.zeros((8, 8, 3), np.uint8)
+        img[..., 2] = v          # BGR on disk: red channel
+        img[..., 0] = 255 - v    # blue channel
+        cv2.imwrite(str(tmp_path / name), img)
+    frames = m._read_frames(tmp_path)
+    assert frames.shape == (3, 3, 8, 8) and frames.dtype == torch.float32
+    assert [round(float(f[0, 0, 0]) * 255) for f in frames] == [10, 20, 100]        # 1, 2, 10 and RGB order
+    assert [round(float(f[2, 0, 0]) * 255) for f in frames] == [245, 235, 155]
