@@ -124,9 +124,25 @@ def rnn_frames(task, lr_pm1, size):
     return VF.normalize(x, -1, 2).clamp(-1, 1)
 
 
+BACKGROUND_WEIGHT = {"x8_bicubic": 0.93, "x16_bicubic": 0.98}   # scripts/video_sample.py:427-444
+
+
+def background_weights(task, init_pm1, face_parse):
+    """model_kwargs["vsrpp_weights"] of the bicubic tasks (scripts/video_sample.py:427-444): the BasicVSR++ branch is
+    damped on pixels the parsing network labels background (class 0).  init_pm1: (T,3,S,S) in [-1,1]; face_parse: the
+    reference's parsing module (output[0] = class logits), caller-supplied PyTorch.  Returns (1,T,1,S,S), or the
+    script's DEFAULT_WEIGHT (1.0) for the other tasks / without a parsing module.  Runs once per window."""
+    bg = BACKGROUND_WEIGHT.get(task)
+    if bg is None or face_parse is None:
+        return 1.0
+    mask = (face_parse(init_pm1)[0].argmax(1, keepdim=True) == 0).float()
+    weight = mask * bg + (1 - mask) * 1.0
+    return weight[None].contiguous()
+
+
 @torch.no_grad()
 def restore_window(model, diffusion, A, task, lr01, *, image_size, prev_recon=None, knobs=None, t_start=-1,
-                   noise_tape=None, generator=None, vsrpp_weights=1.0, aux=None):
+                   noise_tape=None, generator=None, vsrpp_weights=1.0, aux=None, face_parse=None):
     """One window: lr01 (T,3,h,w) in [0,1] on the device -> restored (T,3,S,S) in [-1,1] (fp32, device).
 
     aux: None, or the aux face prior of the reference script (scripts/video_sample.py:446-475) as a dict
@@ -144,6 +160,8 @@ def restore_window(model, diffusion, A, task, lr01, *, image_size, prev_recon=No
     else:
         q_noise, tape = torch.randn(init.shape, device=dev, generator=generator), None
     noise = diffusion.q_sample(init, torch.full((T,), t0, device=dev, dtype=torch.long), noise=q_noise)
+    if face_parse is not None:
+        vsrpp_weights = background_weights(task, init, face_parse)
     model_kwargs = {"low_res_input": init[None], "num_frames": T, "enable_cross_frames": True,
                     "vsrpp_weights": vsrpp_weights}
     rnn = rnn_frames(task, degraded, image_size)
@@ -162,7 +180,7 @@ def restore_window(model, diffusion, A, task, lr01, *, image_size, prev_recon=No
 
 @torch.no_grad()
 def restore_clip(model, diffusion, A, task, lr01, *, image_size, chained=True, knobs=None, noise_tapes=None,
-                 generator=None, overlap=OVERLAP, t_start=-1):
+                 generator=None, overlap=OVERLAP, t_start=-1, face_parse=None):
     """Whole clip: lr01 (N,3,h,w) in [0,1] (device) -> (N,3,S,S) in [0,1].
 
     chained=True reproduces the reference script: windows run in order, every later window is
@@ -172,7 +190,8 @@ def restore_clip(model, diffusion, A, task, lr01, *, image_size, chained=True, k
     for k, (a, b) in enumerate(windows(lr01.shape[0], FRAME_SLICE_LEN, overlap)):
         sample = restore_window(model, diffusion, A, task, lr01[a:b], image_size=image_size,
                                 prev_recon=prev if chained else None, knobs=knobs, t_start=t_start,
-                                noise_tape=None if noise_tapes is None else noise_tapes[k], generator=generator)
+                                noise_tape=None if noise_tapes is None else noise_tapes[k], generator=generator,
+                                face_parse=face_parse)
         keep = sample if k == 0 else sample[overlap:]
         prev = sample[None, -overlap:].clone() if chained else None
         outs.append(((keep.clamp(-1, 1) + 1) / 2))

@@ -99,7 +99,8 @@ def _read_frames(video_path):
 
 
 def main(task, video_path, output_path, device=torch.device("cuda"), t_start=-1, jpeg_qf=-1, w=0.5, tau=5,
-         aligned=False, rho=0.5, noise_level=12.75, zeta=-1, image_size=512, weights="checkpoint", seed=None):
+         aligned=False, rho=0.5, noise_level=12.75, zeta=-1, image_size=512, weights="checkpoint", seed=None,
+         face_parse=None):
     """Restore the frames under `video_path` and write PNGs to `output_path` (reference :265-492).
     `weights="synthetic"` replaces the (offline-unavailable) checkpoint by flair_b200.synth weights."""
     device = torch.device(device)
@@ -130,16 +131,16 @@ def main(task, video_path, output_path, device=torch.device("cuda"), t_start=-1,
     # face_parse=...), affine_matrices=..., w=w, tau=tau, aligned=aligned)).
     print("auxiliary face prior (CodeFormer) is not part of this build: sampling with aux_model=None "
           f"(w={w}, tau={tau}, aligned={aligned} are ignored)")
-    if task in ("x8_bicubic", "x16_bicubic"):
-        print("face-parse background weights (facelib BiSeNet, reference :427-444) are not part of this build: "
-              f"vsrpp_weights={DEFAULT_WEIGHT}")
+    if task in ("x8_bicubic", "x16_bicubic") and face_parse is None:
+        print("no parsing network given (facelib ParseNet is a reference PyTorch module, pass it as face_parse=): "
+              f"background weights of reference :427-444 are off, vsrpp_weights={DEFAULT_WEIGHT}")
     frames = _read_frames(video_path).to(device)
     A_func = get_A_func(task, device, image_size)
     knobs = pipeline.TaskKnobs(rho=rho, noise_level=noise_level, zeta=zeta, jpeg_qf=jpeg_qf,
                                factor=pipeline.KNOBS[task].factor)
     gen = None if seed is None else torch.Generator(device=device).manual_seed(seed)
     out = pipeline.restore_clip(model, diffusion, A_func, task, frames, image_size=image_size, chained=True,
-                                knobs=knobs, generator=gen, t_start=t_start)
+                                knobs=knobs, generator=gen, t_start=t_start, face_parse=face_parse)
     import cv2
     rec = (out * 255).byte().permute(0, 2, 3, 1).cpu().numpy()
     os.makedirs(output_path, exist_ok=True)

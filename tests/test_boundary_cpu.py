@@ -251,3 +251,21 @@ def test_script_reads_frames_in_natural_order(tmp_path):
     assert frames.shape == (3, 3, 8, 8) and frames.dtype == torch.float32
     assert [round(float(f[0, 0, 0]) * 255) for f in frames] == [10, 20, 100]        # 1, 2, 10 and RGB order
     assert [round(float(f[2, 0, 0]) * 255) for f in frames] == [245, 235, 155]
+
+
+def test_background_weights_of_the_bicubic_tasks():
+    """flair_b200.pipeline.background_weights = scripts/video_sample.py:427-444 of the reference: 0.93 (x8) / 0.98 (x16)
+    where the parsing network says background (class 0), 1.0 elsewhere; DEFAULT_WEIGHT for the blur tasks."""
+    from flair_b200 import pipeline
+    T, S = 3, 8
+    logits = torch.zeros(T, 19, S, S)
+    logits[:, 0, :, :4] = 5.0     # left half: background
+    logits[:, 7, :, 4:] = 5.0     # right half: a face class
+    parse = lambda x: (logits, None)
+    init = torch.zeros(T, 3, S, S)
+    for task, bg in (("x8_bicubic", 0.93), ("x16_bicubic", 0.98)):
+        w = pipeline.background_weights(task, init, parse)
+        assert w.shape == (1, T, 1, S, S)
+        assert torch.allclose(w[..., :4], torch.tensor(bg)) and torch.allclose(w[..., 4:], torch.tensor(1.0))
+    assert pipeline.background_weights("gaussian", init, parse) == 1.0
+    assert pipeline.background_weights("x8_bicubic", init, None) == 1.0
