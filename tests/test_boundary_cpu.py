@@ -77,7 +77,20 @@ def test_jpeg_tables(golden):
     fx = golden("dc_jpeg.pt")
     q1, q2 = jpeg.general_quant_matrix(fx["qf"])
     assert torch.equal(q1.reshape(8, 8), fx["q_luma"]) and torch.equal(q2.reshape(8, 8), fx["q_chroma"])
-    assert torch.equal(linear_dct_weight(8, "dct"), fx["dct"]) and torch.equal(linear_dct_weight(8, "idct"), fx["idct"])
+    # The reference builds these weights through torch.fft (dct.py:31-60,167-191), whose last bit depends on the
+    # host CPU's FFT code path (the fixture came from an AVX-512 box; an AVX2-less EPYC differs in 4 entries by
+    # one ulp): <= 1 ulp against the fixture everywhere, and bit-equal to the reference's own module on THIS host
+    # where the checkout exists (build container only).
+    for kind in ("dct", "idct"):
+        w = linear_dct_weight(8, kind)
+        assert (w - fx[kind]).abs().max().item() <= 6e-8, kind
+        ref_py = Path("/root/reference/guided_diffusion/dct.py")
+        if ref_py.exists():
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_reference_dct_for_test", ref_py)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            assert torch.equal(w, mod.LinearDCT(8, kind, norm="ortho").weight.data), kind
 
 
 @pytest.mark.parametrize("task,name,n", [("gaussian", "face_blur", 1000), ("bicubic", "face_bicubic", 2000)])

@@ -57,8 +57,11 @@ def test_jpeg_tables_and_dct(golden):
     fx = golden("dc_jpeg.pt")
     q1, q2 = degrade.quant_tables(fx["qf"])
     assert torch.equal(q1, fx["q_luma"]) and torch.equal(q2, fx["q_chroma"])
-    assert torch.equal(degrade.dct8_matrix(), fx["dct"])
-    assert torch.equal(degrade.idct8_matrix(), fx["idct"])
+    # FFT-route matrices (reference dct.py:31-60): the last bit follows the host's FFT code path, so <= 1 ulp
+    # against the fixture (made on another CPU); tests/test_boundary_cpu.py::test_jpeg_tables checks bit equality
+    # with the reference module run on this host.
+    assert (degrade.dct8_matrix() - fx["dct"]).abs().max().item() <= 6e-8
+    assert (degrade.idct8_matrix() - fx["idct"]).abs().max().item() <= 6e-8
 
 
 def test_jpeg_codec(golden):
