@@ -89,7 +89,8 @@ def _worker_windows(rank, world, port, n_frames, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_frames,world", [(32, 2), (26, 3)])
+# (32, 4) and (64, 8) are the BASELINE strong-scaling layouts bench.py --gpus 4 / 8 runs: one window per rank
+@pytest.mark.parametrize("n_frames,world", [(32, 2), (26, 3), (32, 4), (64, 8)])
 def test_window_sharding_matches_single_process(n_frames, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -105,3 +106,8 @@ def test_window_sharding_matches_single_process(n_frames, world):
     single = parallel.restore_clip_windows(_fake_window, clip, n_frames, torch.device("cpu"), (3, 4, 4), overlap=2)
     assert torch.equal(out, single)          # same bits for any number of ranks
     assert stats["windows"] == len(windows(n_frames, 10, 2)) and stats["p2p_bytes"] > 0
+    if (n_frames, world) in ((32, 4), (64, 8)):
+        assert stats["windows_per_rank_max"] == 1
+        # rank 0 sends every other rank its window (halo included) and receives it back minus the 2 shared frames
+        wins = windows(n_frames, 10, 2)[1:]
+        assert stats["p2p_bytes"] == sum((b - a) + (b - a - 2) for a, b in wins) * 3 * 4 * 4 * 4
