@@ -22,7 +22,11 @@ def windows(n_frames: int, size: int = FRAME_SLICE_LEN, overlap: int = OVERLAP):
     """Frame index ranges produced by more_itertools.windowed(frames, size, step=size-overlap) with the
     None padding filtered (scripts/video_sample.py:361-368)."""
     step = size - overlap
+    if not 0 <= overlap < size:
+        raise ValueError(f"windows: need 0 <= overlap < size, got size={size} overlap={overlap}")
     out, start = [], 0
+    if n_frames <= 0:       # windowed() of an empty sequence yields nothing
+        return out
     while True:
         end = min(start + size, n_frames)
         out.append((start, end))
@@ -187,6 +191,8 @@ def restore_clip(model, diffusion, A, task, lr01, *, image_size, chained=True, k
     hard-conditioned on the previous window's last `overlap` restored frames at every step and
     contributes only its non-overlapping frames (scripts/video_sample.py:369,476-485)."""
     outs, prev = [], None
+    if lr01.shape[0] == 0:  # the reference script dies in torch.cat([]) here; say why
+        raise ValueError("restore_clip: empty clip (no frames to restore)")
     for k, (a, b) in enumerate(windows(lr01.shape[0], FRAME_SLICE_LEN, overlap)):
         sample = restore_window(model, diffusion, A, task, lr01[a:b], image_size=image_size,
                                 prev_recon=prev if chained else None, knobs=knobs, t_start=t_start,

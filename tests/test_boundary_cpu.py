@@ -282,3 +282,17 @@ def test_background_weights_of_the_bicubic_tasks():
         assert torch.allclose(w[..., :4], torch.tensor(bg)) and torch.allclose(w[..., 4:], torch.tensor(1.0))
     assert pipeline.background_weights("gaussian", init, parse) == 1.0
     assert pipeline.background_weights("x8_bicubic", init, None) == 1.0
+
+
+def test_empty_clip_and_bad_windowing_are_loud():
+    """Edge inputs of the windowed driver: an empty clip (the reference script dies in torch.cat([]),
+    scripts/video_sample.py:487) and an overlap that would never advance are explicit errors before any launch."""
+    from flair_b200 import parallel, pipeline
+    assert pipeline.windows(0) == [] and pipeline.windows(1) == [(0, 1)] and pipeline.windows(10) == [(0, 10)]
+    assert pipeline.windows(11) == [(0, 10), (7, 11)]
+    with pytest.raises(ValueError, match="empty clip"):
+        pipeline.restore_clip(None, None, None, "gaussian", torch.empty(0, 3, 16, 16), image_size=64)
+    with pytest.raises(ValueError):
+        pipeline.windows(20, 10, 10)
+    assert parallel.window_plan(0, 4, 10, 2) == [[], [], [], []]
+    assert all(a == b for a, b, _ in parallel.segment_plan(0, 2))

@@ -1,0 +1,91 @@
+"""Ragged window lengths: the reference script's last window of a clip holds 4..10 frames and a short clip is one
+window of 2..9 frames (scripts/video_sample.py:361-368; tests/test_oracle_ops.py::test_pipeline_windows_match_the_script),
+so the video-mode forward must be right for every T, not only the T = 4 / 10 of the reference-made fixtures:
+T = 1 is a one-frame clip (no propagation at all), T = 2 has no second-order propagation, T < 5 never fills TemporalAttention's 5-frame neighbourhood, T = 7 is the
+first length where an interior frame sees four distinct neighbours and every BasicVSR++ branch runs.
+Checked against the CPU oracle (pinned to the reference at T = 4 and T = 10) on identical weights and inputs."""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+S = 64
+CFG = dict(image_size=S, in_channels=6, model_channels=128, out_channels=6, num_res_blocks=1,
+           attention_resolutions=(4,), rnn_resolutions=(1, 2), channel_mult=(0.5, 1, 4), num_head_channels=64,
+           resblock_updown=True, use_scale_shift_norm=True, temporal_block=True)
+
+
+@pytest.fixture(scope="module")
+def pair():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from flair_b200 import synth
+    from guided_diffusion.unet_new import UNetModel
+    from oracle.unet_blur import BlurUNetOracle
+    model = UNetModel(**CFG, use_fp16=True)
+    sd = synth.synthetic_state_dict(model, seed=99)
+    model.load_state_dict(sd)
+    model.convert_to_fp16()
+    model.eval().cuda()
+    return model, BlurUNetOracle(CFG, sd)
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 7, 9])
+def test_video_mode_forward_every_window_length(pair, T):
+    from flair_b200 import synth
+    model, oracle = pair
+    g = torch.Generator().manual_seed(100 + T)
+    x = torch.randn(T, 3, S, S, generator=g)
+    low = synth.synthetic_clip(T, S, seed=40 + T) * 2 - 1
+    t = torch.full((T,), 370)
+    ref = oracle.forward(x, t, low[None], num_frames=T, enable_cross_frames=True, vsrpp_weights=1.0)
+    out = model(x.cuda(), t.cuda(), low_res_input=low[None].cuda(), num_frames=T, enable_cross_frames=True,
+                vsrpp_weights=1.0)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    err = rel_err(out.cpu(), ref)
+    print(f"video-mode T={T} rel L2 vs oracle", err)
+    assert err < 4e-3     # fp16 operands / fp16 stream: the bound tests/test_gpu_unet.py holds the fixtures to
+    # frames of a window are coupled: the same frames inside a different window length must NOT be bit-equal
+    # (guards against a silently per-frame path); only meaningful for T >= 3
+    if T >= 3:
+        sub = model(x[:2].cuda(), t[:2].cuda(), low_res_input=low[None, :2].cuda(), num_frames=2,
+                    enable_cross_frames=True, vsrpp_weights=1.0)
+        assert not torch.equal(sub, out[:2])
+
+
+@pytest.fixture(scope="module")
+def sr3_pair(golden):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from flair_b200 import synth
+    from guided_diffusion.sr3 import UNet
+    from oracle.unet_sr3 import SR3UNetOracle
+    fx = golden("unet_sr3.pt")
+    sd = {k: synth.synthetic_tensor(k, shp, 1234) for k, shp in fx["keys"].items()}
+    model = UNet(**fx["cfg"], dtype=torch.float16)
+    model.load_state_dict(sd)
+    model.convert_to_fp16()
+    model.eval().cuda()
+    return model, SR3UNetOracle(fx["cfg"], sd), fx
+
+
+@pytest.mark.parametrize("T", [2, 5, 9])
+def test_sr3_video_mode_forward_every_window_length(sr3_pair, T):
+    """SR3 (x8 / x16) UNet: TemporalAttention over 7 frames, (3,1,1) temporal convs, BasicVSR++ — T = 9 is the first
+    length whose interior frames see six distinct neighbours."""
+    from flair_b200 import synth
+    model, oracle, fx = sr3_pair
+    Sz = fx["x"].shape[-1]
+    g = torch.Generator().manual_seed(200 + T)
+    x = torch.randn(T, 3, Sz, Sz, generator=g)
+    low = synth.synthetic_clip(T, Sz, seed=60 + T) * 2 - 1
+    level = fx["video_level"][:1].expand(T).contiguous()      # the fixture's continuous noise level, one per frame
+    ref = oracle.forward(x, level, low[None], num_frames=T, enable_cross_frames=True, vsrpp_weights=1.0)
+    out = model(x.cuda(), level.cuda(), low_res_input=low[None].cuda(), num_frames=T, enable_cross_frames=True,
+                vsrpp_weights=1.0)
+    assert out.shape == ref.shape
+    err = rel_err(out.cpu(), ref)
+    print(f"sr3 video-mode T={T} rel L2 vs oracle", err)
+    assert err < 4e-3

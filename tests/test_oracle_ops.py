@@ -127,3 +127,31 @@ def test_sampler_loop(golden):
     out = sampler.sample_loop(tab, toy, fx["x_start"], tape[1:], restore, rho=0.25, zeta=1.0, noise_level=2.55,
                               t_start=5)
     assert rel_err(out, fx["final"]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ windowing
+def test_windowed_restatement_known_answers():
+    """oracle/windowing.windowed against the documented examples of more_itertools.windowed."""
+    from oracle.windowing import windowed
+    assert list(windowed([1, 2, 3, 4, 5], 3)) == [(1, 2, 3), (2, 3, 4), (3, 4, 5)]
+    assert list(windowed([1, 2, 3], 4)) == [(1, 2, 3, None)]
+    assert list(windowed([1, 2, 3, 4, 5, 6], 3, fillvalue="!", step=2)) == [(1, 2, 3), (3, 4, 5), (5, 6, "!")]
+    assert list(windowed([1, 2, 3, 4, 5, 6, 7, 8], 3, step=4)) == [(1, 2, 3), (5, 6, 7)]   # step > n skips items
+    assert list(windowed([], 3)) == []
+    assert list(windowed([1, 2], 0)) == [()]
+
+
+@pytest.mark.parametrize("size,overlap", [(10, 3), (10, 2), (4, 1), (5, 0), (3, 2)])
+def test_pipeline_windows_match_the_script(size, overlap):
+    """flair_b200.pipeline.windows == the reference script's windowing for every clip length, ragged tails included;
+    stitching (drop `overlap` frames of every later window) yields every frame exactly once, in order."""
+    from flair_b200.pipeline import windows
+    from oracle.windowing import script_stitch, script_windows
+    for n in range(0, 81):
+        want = script_windows(n, size, overlap)
+        got = windows(n, size, overlap)
+        assert [list(range(a, b)) for a, b in got] == want, (n, got, want)
+        assert script_stitch(want, overlap) == list(range(n)), n
+        assert all(len(w) > overlap for w in want[1:]), n     # a later window always contributes >= 1 frame
+    with pytest.raises(ValueError):
+        windows(5, size, size)
