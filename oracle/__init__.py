@@ -14,6 +14,9 @@ un-vendored mmedit==0.12.0 / mmcv-full==1.4.8 (SPyNet, flow_warp,
 ResidualBlocksWithInputConv, ModulatedDeformConv2d) are restated from their
 published behaviour: **parity unpinned** for those (video-mode BasicVSR++ only).
 
+`windowing.py` restates `more_itertools.windowed` (requirements.txt:8, un-vendored,
+unpinned) from its published algorithm and documented examples.
+
 Every function cites the reference file:line it follows (paths relative to the
 reference checkout).
 """
