@@ -296,3 +296,38 @@ def test_empty_clip_and_bad_windowing_are_loud():
         pipeline.windows(20, 10, 10)
     assert parallel.window_plan(0, 4, 10, 2) == [[], [], [], []]
     assert all(a == b for a, b, _ in parallel.segment_plan(0, 2))
+
+
+def test_c_abi_rejects_bad_arguments_before_any_launch():
+    """Error convention of the C ABI (include/flair_b200.h): argument validation comes first, returns
+    FLAIR_ERR_INVALID (-1) and leaves a message in flair_last_error(); nothing is launched, so this runs without a
+    GPU.  The fake non-null pointers are never dereferenced (host side) nor passed to a kernel."""
+    from flair_b200 import _lib as L
+    lib = L.lib()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+
+    def err():
+        return lib.flair_last_error().decode()
+
+    assert lib.flair_blur_down_f32(None, p, p, 9, 4, 1, 3, 64, 64, None) == -1 and "null pointer" in err()
+    assert lib.flair_blur_down_f32(p, p, p, 9, 4, 1, 3, 66, 64, None) == -1 and "bad geometry" in err() and "H=66" in err()
+    assert lib.flair_blur_down_f32(p, p, p, 8, 4, 1, 3, 64, 64, None) == -1 and "k=8" in err()       # even tap count
+    assert lib.flair_jpeg_f32(5, p, p, p, p, p, p, p, p, 1, 64, 64, None) == -1 and "mode must be 0, 1 or 2" in err()
+    assert lib.flair_jpeg_f32(2, p, None, None, p, p, p, p, p, 1, 24, 64, None) == -1       # 24 is not a multiple of 16
+    assert lib.flair_jpeg_f32(0, p, None, None, None, p, p, p, p, 1, 64, 64, None) == -1 and "planes are NULL" in err()
+    assert lib.flair_axpby_f32(p, p, 1.0, 1.0, p, 6, None) == -1 and "multiple of 4" in err()
+    assert lib.flair_pred_xstart_f32(p, None, 3, p, None, 0, p, 1, 8, 8, 1, None) == -1 and "null pointer" in err()
+    assert lib.flair_dc_apply_f32(None, p, None, 1.0, p, 1, 8, 8, 1, None) == -1
+    u = L.UpdateParams()
+    assert lib.flair_sampler_update_f32(ctypes.byref(u), None) == -1                         # all pointers NULL
+    u.x_t = u.model_out = u.noise = u.coef = u.sample = p.value
+    u.model_ch, u.N, u.H, u.W = 4, 1, 8, 8
+    assert lib.flair_sampler_update_f32(ctypes.byref(u), None) == -1                         # 3 or 6 model channels only
+    u.model_ch = 6
+    u.R = u.q_lr = p.value
+    assert lib.flair_sampler_update_f32(ctypes.byref(u), None) == -1 and "not both" in err()
+    c = L.ConvParams()
+    assert lib.flair_conv_igemm(ctypes.byref(c), None) != 0 and err()
+    with pytest.raises(RuntimeError, match=r"flair_b200: .*rc=-1"):
+        L.check(lib.flair_axpby_f32(p, p, 1.0, 1.0, p, 6, None))
