@@ -331,3 +331,34 @@ def test_c_abi_rejects_bad_arguments_before_any_launch():
     assert lib.flair_conv_igemm(ctypes.byref(c), None) != 0 and err()
     with pytest.raises(RuntimeError, match=r"flair_b200: .*rc=-1"):
         L.check(lib.flair_axpby_f32(p, p, 1.0, 1.0, p, 6, None))
+
+
+def test_missing_library_is_a_loud_error(monkeypatch, tmp_path):
+    """No CPU / PyTorch fallback: without the built .so the binding raises (it does not degrade)."""
+    from flair_b200 import _lib as L
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "_LIB_PATH", tmp_path / "libflair_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        L.lib()
+
+
+def test_product_never_imports_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke()/build() and bench.py's CPU legs may import
+    it; /root/reference must not be read by anything that runs on the GPU box (product, tests, bench, smoke)."""
+    imp = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    product = [p for d in ("flair_b200", "guided_diffusion", "scripts") for p in (ROOT / d).rglob("*.py")]
+    assert len(product) > 20
+    for p in product:
+        src = p.read_text()
+        assert not imp.search(src), f"{p.relative_to(ROOT)} imports oracle"
+        assert "/root/reference" not in src, f"{p.relative_to(ROOT)} names the reference checkout"
+    # bench.py: the oracle only inside the CPU arm (cpu_config1_factory), never in the native path
+    bench = (ROOT / "bench.py").read_text()
+    reads_ref = re.compile(r"(Path|open|insert|append|load|chdir)\([^)\n]*/root/reference")
+    assert not reads_ref.search(bench), "bench.py reads the reference checkout"   # (it only names it in a note)
+    native = bench[bench.index("class Job"):]
+    assert not imp.search(native), "bench.py's native arm imports oracle"
+    # GPU tests and smoke may use the oracle as the checker but must not touch the reference checkout; the one CPU
+    # test that does (test_jpeg_tables, this file) guards it with .exists()
+    for p in list((ROOT / "tests").glob("test_gpu_*.py")) + [ROOT / "__graft_entry__.py"]:
+        assert "/root/reference" not in p.read_text(), p.name
