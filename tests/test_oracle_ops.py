@@ -155,3 +155,50 @@ def test_pipeline_windows_match_the_script(size, overlap):
         assert all(len(w) > overlap for w in want[1:]), n     # a later window always contributes >= 1 frame
     with pytest.raises(ValueError):
         windows(5, size, size)
+
+
+# ------------------------------------------------------------------------------------------------ operator properties
+def test_blur_data_consistency_properties(golden):
+    """Size-independent properties of the blur operator's correction R = A_pinv(y, x) (pseudoSR.py:248-281): x that
+    already explains y is a fixed point (R == 0 exactly), R is linear in (x, y), and ONE full correction makes the
+    observation hold: Down(x - R) == y away from the replicate-padded border ring."""
+    ds, inv = _taps(golden)
+    g = torch.Generator().manual_seed(0)
+    R = lambda x, y: degrade.blur_restore(x, y, ds, inv)
+    S = 128
+    x, x2, z = (torch.rand(1, 3, S, S, generator=g) * 2 - 1 for _ in range(3))
+    y, y2 = degrade.blur_down(z, ds), torch.rand(1, 3, S // 4, S // 4, generator=g)
+    assert float(R(z, y).abs().max()) == 0.0
+    assert rel_err(R(0.3 * x - 1.7 * x2, 0.3 * y - 1.7 * y2), 0.3 * R(x, y) - 1.7 * R(x2, y2)) < 5e-6
+    before = degrade.blur_down(x, ds) - y
+    after = degrade.blur_down(x - R(x, y), ds) - y
+    assert float(before.abs().max()) > 0.5
+    assert float(after[..., 1:-1, 1:-1].abs().max()) < 5e-6      # interior: the truncated inverse filter is exact to fp32
+    assert float(after.abs().max()) < 0.2                        # border ring: replicate padding, not a projection
+
+
+def test_jpeg_codec_is_idempotent(golden):
+    """encode(decode(encode(x))) == encode(x): a decoded image re-quantises to the same integer coefficients
+    (jpeg.py:72-167), so the JPEG data-consistency step leaves an already consistent estimate alone."""
+    fx = golden("dc_jpeg.pt")
+    e1 = degrade.jpeg_encode(fx["img"], fx["qf"])
+    d1 = degrade.jpeg_decode(e1, fx["qf"])
+    e2 = degrade.jpeg_encode(d1, fx["qf"])
+    assert torch.equal(e1[0], e2[0]) and torch.equal(e1[1], e2[1])
+    assert torch.equal(e1[0], e1[0].round()) and torch.equal(e1[1], e1[1].round())     # integer planes
+    assert torch.equal(degrade.jpeg_decode(e2, fx["qf"]), d1)
+
+
+@pytest.mark.parametrize("factor", [8, 16])
+def test_srconv_projection_properties(golden, factor):
+    """bicubic_restore (scripts/video_sample.py:177-181): after x <- x - A^+(A x - y) the observation holds exactly
+    (A A^+ = I: all singular values non-zero) and a second correction is zero (idempotent projection)."""
+    fx = golden(f"dc_srconv_x{factor}.pt")
+    U, S, V = fx["U"], fx["S"], fx["V"]
+    small = U.shape[0]
+    V1, ss = V[:, :small], S[:, None] * S[None, :]
+    A = lambda X: U @ (ss * (V1.t() @ X @ V1)) @ U.t()
+    x, y = fx["x"], fx["y"]
+    x1 = x - degrade.srconv_restore(x, y, U, S, V)
+    assert rel_err(A(x), y) > 1e-2 and rel_err(A(x1), y) < 2e-6
+    assert float(degrade.srconv_restore(x1, y, U, S, V).abs().max()) < 5e-6
