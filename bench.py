@@ -249,6 +249,12 @@ class Job:
                                        generator=g)
 
 
+def _launch_count():
+    """C-ABI launch calls issued so far by this process (a replayed CUDA graph adds the launches it captured)."""
+    from flair_b200 import _lib as L
+    return L.LAUNCHES[0]
+
+
 def _timed_steps(n_steps, barrier, body):
     """body(k, ev) records ev[0..3] around H2D / compute / D2H; returns (inner_s, outer_s) summed over steps."""
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_steps)]
@@ -275,10 +281,12 @@ def run_replicas(job, steps, warmup, world, barrier, reduce_max):
         job.out_host.copy_(out, non_blocking=True)            # D2H of the restored frames
         e[3].record()
 
+    n0 = _launch_count()
     inner, outer = reduce_max(*_timed_steps(steps, barrier, body))
+    launches = _launch_count() - n0                          # C-ABI launches of THIS rank inside the timed region
     total = job.frames * world * steps
     return dict(value=total / inner, e2e=total / outer, ms_per_step=inner / steps * 1e3,
-                h2d=job.lr_host.numel() * 4, d2h=job.out_host.numel() * 4)
+                h2d=job.lr_host.numel() * 4, d2h=job.out_host.numel() * 4, launches=launches)
 
 
 def run_sharded(job, steps, warmup, world, rank, barrier, reduce_max):
@@ -305,10 +313,12 @@ def run_sharded(job, steps, warmup, world, rank, barrier, reduce_max):
             job.out_host.copy_(out, non_blocking=True)
         e[3].record()
 
+    n0 = _launch_count()
     inner, outer = reduce_max(*_timed_steps(steps, barrier, body))
+    launches = _launch_count() - n0
     total = job.frames * steps
     return dict(value=total / inner, e2e=total / outer, ms_per_step=inner / steps * 1e3,
-                h2d=job.lr_host.numel() * 4, d2h=job.out_host.numel() * 4,
+                h2d=job.lr_host.numel() * 4, d2h=job.out_host.numel() * 4, launches=launches,
                 p2p_bytes_per_step=stats.get("p2p_bytes", 0), windows=stats.get("windows"),
                 windows_per_rank_max=stats.get("windows_per_rank_max"),
                 compute_s_max_rank=reduce_max(stats.get("compute_s", 0.0), 0.0)[0])
@@ -355,13 +365,12 @@ def run_native(args):
 
     mode = args.mode if args.mode != "auto" else "replicas"
     job = Job(args.workload, dev, seed_offset=rank if mode == "replicas" else 0)
-    n0 = L.LAUNCHES[0]
     with ClockSampler(local) as clocks:
         if mode == "replicas":
             res = run_replicas(job, args.steps, args.warmup, world, barrier, reduce_max)
         else:
             res = run_sharded(job, args.steps, args.warmup, world, rank, barrier, reduce_max)
-    launches = L.LAUNCHES[0] - n0
+    launches = res["launches"]      # rank 0's launches inside the timed region (warm-up steps excluded)
 
     strong = []
     if args.mode == "auto" and world > 1:
