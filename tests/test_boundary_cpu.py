@@ -362,3 +362,33 @@ def test_product_never_imports_the_oracle_or_the_reference():
     # test that does (test_jpeg_tables, this file) guards it with .exists()
     for p in list((ROOT / "tests").glob("test_gpu_*.py")) + [ROOT / "__graft_entry__.py"]:
         assert "/root/reference" not in p.read_text(), p.name
+
+
+def test_sampler_argument_errors_match_the_reference():
+    """Error behaviour of the sampler API before anything reaches the device: the reference's asserts
+    (gaussian_diffusion.py:129-130,219,233,276,621) and its t_start ValueError (:629) are kept."""
+    from flair_b200 import pipeline
+    from guided_diffusion import gaussian_diffusion as gd
+    kw = dict(model_mean_type=gd.ModelMeanType.EPSILON, model_var_type=gd.ModelVarType.FIXED_SMALL,
+              loss_type=gd.LossType.MSE)
+    with pytest.raises(AssertionError, match="1-D"):
+        gd.GaussianDiffusion(betas=np.full((2, 3), 0.1), **kw)
+    with pytest.raises(AssertionError):
+        gd.GaussianDiffusion(betas=np.array([0.1, 0.0, 0.2]), **kw)
+    with pytest.raises(AssertionError):
+        gd.GaussianDiffusion(betas=np.array([0.1, 1.5]), **kw)
+    with pytest.raises(NotImplementedError, match="unknown beta schedule"):
+        gd.get_named_beta_schedule("cosine-ish", 10)
+    d = pipeline.make_diffusion("gaussian")
+    assert d.num_timesteps == 100
+    x = torch.zeros(2, 3, 8, 8)
+    with pytest.raises(AssertionError):
+        d.q_sample(x, torch.zeros(2, dtype=torch.long), noise=torch.zeros(2, 3, 8, 4))
+    with pytest.raises(AssertionError):
+        d.q_posterior_mean_variance(x, torch.zeros(2, 3, 8, 4), torch.zeros(2, dtype=torch.long))
+    model = torch.nn.Linear(1, 1)       # only .parameters() is consulted before the argument checks
+    with pytest.raises(AssertionError, match="tuple or list"):
+        next(d.p_sample_loop_progressive(model, "2x3x8x8", noise=x))
+    for bad in (100, 250, -2):
+        with pytest.raises(ValueError, match="t_start"):
+            next(d.p_sample_loop_progressive(model, (2, 3, 8, 8), noise=x, t_start=bad))
