@@ -71,3 +71,38 @@ def test_temporal_attention_isolated(golden, name):
     m.p = lambda n: sd[n].float()
     out = m.temporal_attention(fx["x"], "ta", frames=fx[name]["frames"])
     assert rel_err(out, fx[name]["out"]) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ ragged windows
+@pytest.fixture(scope="module")
+def ragged(golden):
+    from oracle.unet_sr3 import SR3UNetOracle
+    fx = golden("unet_ragged.pt")
+    from guided_diffusion.unet_new import UNetModel
+    blur_sd = synth.synthetic_state_dict(UNetModel(**fx["blur_cfg"], use_fp16=False), seed=fx["blur_weights_seed"])
+    keys = golden("unet_sr3.pt")["keys"]
+    sr3_sd = {k: synth.synthetic_tensor(k, shp, fx["sr3_weights_seed"]) for k, shp in keys.items()}
+    return fx, BlurUNetOracle(fx["blur_cfg"], blur_sd), SR3UNetOracle(fx["sr3_cfg"], sr3_sd)
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 7, 9])
+def test_video_mode_every_window_length(ragged, T):
+    """tests/golden/unet_ragged.pt (tools/gen_golden_big.py ragged: the unmodified reference at every window length the
+    script can produce) pins the oracle at T != 4, 10; tests/test_gpu_ragged.py runs the GPU path on the same seeds."""
+    fx, blur, _ = ragged
+    S = fx["size"]
+    x = torch.randn(T, 3, S, S, generator=torch.Generator().manual_seed(100 + T))
+    low = synth.synthetic_clip(T, S, seed=40 + T) * 2 - 1
+    out = blur.forward(x, torch.full((T,), fx["t"]), low[None], num_frames=T, enable_cross_frames=True, vsrpp_weights=1.0)
+    assert rel_err(out, fx["blur"][T]) < 2e-5
+
+
+@pytest.mark.parametrize("T", [2, 5, 9])
+def test_sr3_video_mode_every_window_length(ragged, T):
+    fx, _, sr3 = ragged
+    S = fx["size"]
+    x = torch.randn(T, 3, S, S, generator=torch.Generator().manual_seed(200 + T))
+    low = synth.synthetic_clip(T, S, seed=60 + T) * 2 - 1
+    out = sr3.forward(x, torch.full((T,), fx["level"]), low[None], num_frames=T, enable_cross_frames=True,
+                      vsrpp_weights=1.0)
+    assert rel_err(out, fx["sr3"][T]) < 2e-5

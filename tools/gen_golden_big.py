@@ -5,6 +5,7 @@
   python tools/gen_golden_big.py sr3_256      # sr3.UNet video mode, T=10, 256x256, image_size=256 config
   python tools/gen_golden_big.py sampler jpeg|x8_bicubic|x16_bicubic   # 100-step reference sampler, T=4, 64x64
   python tools/gen_golden_big.py tattn        # isolated TemporalAttention modules (unet_new F=5, unet F=7), T=9
+  python tools/gen_golden_big.py ragged       # video-mode forwards at T = 1..9 (blur) / 2, 5, 9 (SR3), 64x64
 
 Inputs are functions of seeds (flair_b200.synth) so the fixtures hold only the seeds and the reference OUTPUT
 (fp16 for the 256x256 forwards: 2^-11 relative rounding against a 1e-2 tolerance)."""
@@ -96,6 +97,46 @@ def sr3_256():
     torch.save({"cfg": cfg, "size": S, "frames": T, "x_seed": 131, "clip_seed": 16, "level": 0.37,
                 "weights_seed": 1234, "out_f16": out.half(), "out_norm": float(out.double().norm()),
                 "cpu_seconds": time.time() - t0, "cores": torch.get_num_threads()}, OUT / "unet_sr3_256.pt")
+
+
+RAGGED_BLUR_CFG = dict(image_size=64, in_channels=6, model_channels=128, out_channels=6, num_res_blocks=1,
+                       attention_resolutions=(4,), rnn_resolutions=(1, 2), channel_mult=(0.5, 1, 4), num_head_channels=64,
+                       resblock_updown=True, use_scale_shift_norm=True, temporal_block=True)
+
+
+def ragged():
+    """Video-mode forward of the UNMODIFIED reference at every window length the script can produce (a short clip is
+    one window of 1..9 frames, the last window of a clip holds 4..10): pins the oracle — and through it the GPU path,
+    tests/test_gpu_ragged.py uses the same seeds — at T != 4, 10.  Outputs only (inputs are functions of seeds)."""
+    import guided_diffusion.sr3 as rsr3
+    import guided_diffusion.unet_new as runet
+    S = 64
+    fx = {"blur": {}, "sr3": {}, "blur_cfg": RAGGED_BLUR_CFG, "sr3_cfg": dict(SR3_CFG_64), "blur_weights_seed": 99,
+          "sr3_weights_seed": 1234, "t": 370, "level": 0.37, "size": S}
+    model = _with_cuda_flag(lambda: runet.UNetModel(**RAGGED_BLUR_CFG, use_fp16=False, use_checkpoint=False))
+    model.eval()
+    model.load_state_dict(synth.synthetic_state_dict(model, seed=99))
+    for T in (1, 2, 3, 5, 7, 9):
+        x = torch.randn(T, 3, S, S, generator=torch.Generator().manual_seed(100 + T))
+        low = synth.synthetic_clip(T, S, seed=40 + T) * 2 - 1
+        t0 = time.time()
+        out = model(x, torch.full((T,), 370), low_res_input=low[None], num_frames=T, enable_cross_frames=True,
+                    vsrpp_weights=1.0)
+        fx["blur"][T] = out.clone()
+        print("ragged blur T =", T, tuple(out.shape), float(out.std()), f"{time.time() - t0:.1f} s")
+    model = _with_cuda_flag(lambda: rsr3.UNet(**SR3_CFG_64, spatial_attn=False, dropout=0.0, dtype=torch.float32,
+                                              use_checkpoint=False))
+    model.eval()
+    keys = torch.load(OUT / "unet_sr3.pt", weights_only=True)["keys"]
+    model.load_state_dict({k: synth.synthetic_tensor(k, shp, 1234) for k, shp in keys.items()})
+    for T in (2, 5, 9):
+        x = torch.randn(T, 3, S, S, generator=torch.Generator().manual_seed(200 + T))
+        low = synth.synthetic_clip(T, S, seed=60 + T) * 2 - 1
+        out = model(x, torch.full((T,), 0.37), low_res_input=low[None], num_frames=T, enable_cross_frames=True,
+                    vsrpp_weights=1.0)
+        fx["sr3"][T] = out.clone()
+        print("ragged sr3 T =", T, tuple(out.shape), float(out.std()))
+    torch.save(fx, OUT / "unet_ragged.pt")
 
 
 def _bicubic_kernel(factor):
@@ -262,5 +303,7 @@ if __name__ == "__main__":
         sampler(sys.argv[2])
     elif what == "tattn":
         tattn()
+    elif what == "ragged":
+        ragged()
     else:
         raise SystemExit(__doc__)
