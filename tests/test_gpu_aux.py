@@ -102,3 +102,8 @@ def test_p_sample_aux_unaligned_vs_oracle(dev, golden):
     ref = c_ * x0 + (float(np.sqrt(1 - rho)) * d_ * eps_hat + float(np.sqrt(rho)) * d_ * noise)
     assert rel_err(out["pred_xstart"].cpu(), x0) < 1e-5
     assert rel_err(out["sample"].cpu(), ref) < 1e-5
+    # the same step run by the UNMODIFIED reference p_sample through its own FaceRestoreHelper + cv2
+    # (tests/golden/aux_psample.pt; the composition above is within 1.5e-8 of it, tests/test_oracle_aux.py)
+    fx = golden("aux_psample.pt")["unaligned"]
+    assert rel_err(out["pred_xstart"].cpu(), fx["pred_xstart"]) < 1.5e-5
+    assert rel_err(out["sample"].cpu(), fx["sample"]) < 1.5e-5

@@ -247,6 +247,11 @@ def test_p_sample_aux_branch_vs_oracle(dev, golden):
     ref = c * x0 + (float(np.sqrt(1 - rho)) * dd * eps_hat + float(np.sqrt(rho)) * dd * noise)
     assert rel_err(out["pred_xstart"].cpu(), x0) < 1e-5
     assert rel_err(out["sample"].cpu(), ref) < 1e-5
+    # the same step run by the UNMODIFIED reference p_sample (tests/golden/aux_psample.pt, tools/gen_golden_aux.py psample;
+    # the composition above equals it bit for bit: tests/test_oracle_aux.py::test_aux_prior_sampling_step_matches_reference)
+    fx = golden("aux_psample.pt")["aligned"]
+    assert rel_err(out["pred_xstart"].cpu(), fx["pred_xstart"]) < 1e-5
+    assert rel_err(out["sample"].cpu(), fx["sample"]) < 1e-5
 
 
 # ---------------------------------------------------------------------------------------------- graphed step

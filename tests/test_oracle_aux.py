@@ -45,3 +45,19 @@ def test_helper_host_side(golden):
     assert frh.MASK_COLORMAP == fw.MASK_COLORMAP and frh.CROP_BORDER == fw.CROP_BORDER
     with pytest.raises(RuntimeError):
         frh.FaceRestoreHelper(device="cpu")
+
+
+def test_aux_prior_sampling_step_matches_reference(golden):
+    """The aux-prior branch of p_sample (reference gaussian_diffusion.py:465-515): the oracle compositions the GPU tests
+    check against (tests/aux_inputs.py) versus the UNMODIFIED reference p_sample on the same seeded inputs
+    (tests/golden/aux_psample.pt, tools/gen_golden_aux.py psample) — aligned=True with blur data consistency, and
+    aligned=False through the reference FaceRestoreHelper + cv2."""
+    import aux_inputs as ai
+    from conftest import rel_err
+    fx = golden("aux_psample.pt")
+    x0, sample = ai.aligned_oracle(ai.aligned_case())
+    ea = rel_err(x0, fx["aligned"]["pred_xstart"]), rel_err(sample, fx["aligned"]["sample"])
+    x0, sample = ai.unaligned_oracle(ai.unaligned_case())
+    eu = rel_err(x0, fx["unaligned"]["pred_xstart"]), rel_err(sample, fx["unaligned"]["sample"])
+    print("aux p_sample, oracle vs reference: aligned", ea, "unaligned", eu)
+    assert max(ea) < 2e-6 and max(eu) < 2e-6

@@ -3,7 +3,8 @@
 (/root/reference/guided_diffusion/facelib/utils/face_restoration_helper.py:225-345) with the build container's
 OpenCV (cv2 4.13.0) on CPU.
 
-  python tools/gen_golden_aux.py      ->  tests/golden/aux_warp.pt
+  python tools/gen_golden_aux.py            ->  tests/golden/aux_warp.pt
+  python tools/gen_golden_aux.py psample    ->  tests/golden/aux_psample.pt  (reference p_sample with the prior active)
 
 The helper object is created without running its constructor (which downloads the RetinaFace / ParseNet checkpoints:
 no network here); `face_parse` is a stand-in returning fixed, seeded logits (the real parsing network is a reference
@@ -76,7 +77,57 @@ def run_case(img, face, n, stride):
                 frames_seed=(21, 22), faces_seed=23, logits_seed=7 + face)
 
 
+def psample():
+    """The aux-prior branch of the UNMODIFIED reference `GaussianDiffusion.p_sample` (gaussian_diffusion.py:423-517) on
+    the exact inputs of the two GPU tests of that branch (tests/aux_inputs.py: aligned_case / unaligned_case), so the
+    oracle compositions those tests use are pinned to the reference -> tests/golden/aux_psample.pt (outputs only)."""
+    import numpy as np
+    from scipy.io import loadmat
+    import guided_diffusion.gaussian_diffusion as gd
+    import guided_diffusion.pseudoSR as rpsr
+    from guided_diffusion.respace import SpacedDiffusion, space_timesteps
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+    import aux_inputs as ai
+    assert "/root/reference" in gd.__file__
+    d = SpacedDiffusion(use_timesteps=space_timesteps(1000, "100", "uniform"),
+                        betas=gd.get_named_beta_schedule("face_blur", 1000), noise_schedule="face_blur",
+                        model_mean_type=gd.ModelMeanType.EPSILON, model_var_type=gd.ModelVarType.LEARNED_RANGE,
+                        loss_type=gd.LossType.MSE, rescale_timesteps=False)
+    out = {}
+    # ---- aligned=True, blur data consistency with a per-frame gamma (tests/test_gpu_round2.py)
+    c = ai.aligned_case()
+    kernel = loadmat("/root/reference/miscs/kernels_12.mat")["kernels"]
+    conf = rpsr.Get_pseudoSR_Conf(4); conf.sigmoid_range_limit = False; conf.input_range = np.array(None)
+    A = rpsr.pseudoSR(conf, upscale_kernel=kernel[0, 3], kernel_indx=10).WrapArchitecture_PyTorch()
+    gd.th.randn_like = lambda t: c["noise"].clone()
+    N = c["x_t"].shape[0]
+    r = d.p_sample(lambda xx, ts, **kw: c["mout"].clone(), c["x_t"].clone(), torch.full((N,), c["t"]), model_kwargs={},
+                   restore_fn=lambda v: A.A_pinv(c["y"], v), aux_model=c["aux"], w=c["w"], start_timestep=99, tau=5,
+                   aligned=True, rho=c["rho"], gamma=torch.full((N, 1, 1, 1), float(c["gamma"]), dtype=torch.float32),
+                   face_restore_helper=None, affine_matrices=None)
+    out["aligned"] = {"sample": r["sample"].clone(), "pred_xstart": r["pred_xstart"].clone()}
+    # ---- aligned=False: crops -> aux -> inverse warps + parsing mask -> blend, through the reference helper + cv2
+    u = ai.unaligned_case()
+    helper = object.__new__(ref_frh.FaceRestoreHelper)
+    helper.face_size = (u["S"], u["S"])
+    helper.device = torch.device("cpu")
+    logits = torch.from_numpy(u["logits"])
+    helper.face_parse = lambda x: (logits,)
+    gd.th.randn_like = lambda t: u["noise"].clone()
+    N = u["x_t"].shape[0]
+    r = d.p_sample(lambda xx, ts, **kw: u["mout"].clone(), u["x_t"].clone(), torch.full((N,), u["t"]), model_kwargs={},
+                   aux_model=u["aux"], face_restore_helper=helper, affine_matrices=u["Ms"], w=u["w"], start_timestep=99,
+                   tau=5, aligned=False, rho=u["rho"])
+    out["unaligned"] = {"sample": r["sample"].clone(), "pred_xstart": r["pred_xstart"].clone()}
+    out["cv2_version"] = cv2.__version__
+    torch.save(out, OUT / "aux_psample.pt")
+    print("wrote", OUT / "aux_psample.pt", (OUT / "aux_psample.pt").stat().st_size / 1e6, "MB")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "psample":
+        psample()
+        raise SystemExit(0)
     fx = dict(cv2_version=cv2.__version__, cases=[run_case(256, 256, 1, 1), run_case(256, 512, 2, 4),
                                                   run_case(512, 512, 1, 4)])
     # the blend of gaussian_diffusion.py:488-496 on the first case, in torch like the reference writes it
