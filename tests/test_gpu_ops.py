@@ -49,6 +49,9 @@ def test_blur_restore_vs_oracle_256(dev, golden, blur_op):
     y = degrade.blur_down(hr, ds)
     R = blur_op.A_pinv(y.to(dev), x.to(dev)).cpu()
     assert rel_err(R, degrade.blur_restore(x, y, ds, inv)) < 1e-5
+    # and against the UNMODIFIED reference operator on the same inputs (tests/golden/dc_gaussian_256.pt; the oracle is
+    # bit-equal to it on the fixture's host, tests/test_oracle_ops.py::test_blur_restore_at_the_benchmarked_size)
+    assert rel_err(R, golden("dc_gaussian_256.pt")["R"]) < 1e-5
     # linearity: R(x; y) - R(x'; y) == R(x - x'; 0)
     x2 = x.flip(0)
     lhs = blur_op.A_pinv(y.to(dev), x.to(dev)) - blur_op.A_pinv(y.to(dev), x2.to(dev))

@@ -44,6 +44,21 @@ def test_blur_restore(golden):
     assert rel_err(degrade.blur_restore(fx["x"], fx["y"], ds, inv), fx["R"]) < 1e-5
 
 
+def test_blur_restore_at_the_benchmarked_size(golden):
+    """256 x 256 (BASELINE size): the oracle against the UNMODIFIED reference operator on the seeded inputs of
+    tests/test_gpu_ops.py::test_blur_restore_vs_oracle_256 (tests/golden/dc_gaussian_256.pt, gen_golden_big.py ops256)."""
+    from flair_b200 import synth
+    fx = golden("dc_gaussian_256.pt")
+    ds, inv = _taps(golden)
+    hr = synth.synthetic_clip(fx["frames"], fx["size"], seed=fx["hr_seed"]) * 2 - 1
+    x = (hr + 0.2 * torch.randn(hr.shape, generator=torch.Generator().manual_seed(fx["noise_seed"]))).clamp(-1, 1)
+    y = degrade.blur_down(hr, ds)
+    assert rel_err(y, fx["down_hr"]) < 1e-6          # (bit-equal on the host that made the fixture)
+    err = rel_err(degrade.blur_restore(x, y, ds, inv), fx["R"])
+    print("oracle vs reference, blur restore at 256:", err)
+    assert err < 1e-6
+
+
 def test_filter_weights_are_the_taps(golden):
     t = golden("pseudosr_taps.pt")
     ds, inv = _taps(golden)

@@ -5,6 +5,7 @@
   python tools/gen_golden_big.py sr3_256      # sr3.UNet video mode, T=10, 256x256, image_size=256 config
   python tools/gen_golden_big.py sampler jpeg|x8_bicubic|x16_bicubic   # 100-step reference sampler, T=4, 64x64
   python tools/gen_golden_big.py tattn        # isolated TemporalAttention modules (unet_new F=5, unet F=7), T=9
+  python tools/gen_golden_big.py ops256       # blur data-consistency operator at 256x256 (3 frames)
   python tools/gen_golden_big.py ragged       # video-mode forwards at T = 1..9 (blur) / 2, 5, 9 (SR3), 64x64
 
 Inputs are functions of seeds (flair_b200.synth) so the fixtures hold only the seeds and the reference OUTPUT
@@ -137,6 +138,29 @@ def ragged():
         fx["sr3"][T] = out.clone()
         print("ragged sr3 T =", T, tuple(out.shape), float(out.std()))
     torch.save(fx, OUT / "unet_ragged.pt")
+
+
+def ops256():
+    """The blur data-consistency operator of the UNMODIFIED reference (pseudoSR.py:248-281) at the BENCHMARKED size:
+    A_pinv(y, x) on 3 frames of 256x256, inputs exactly those of tests/test_gpu_ops.py::test_blur_restore_vs_oracle_256
+    (functions of seeds) -> tests/golden/dc_gaussian_256.pt (outputs only)."""
+    from scipy.io import loadmat
+    import guided_diffusion.pseudoSR as rpsr
+    from oracle import degrade
+    kernel = loadmat("/root/reference/miscs/kernels_12.mat")["kernels"]
+    conf = rpsr.Get_pseudoSR_Conf(4); conf.sigmoid_range_limit = False; conf.input_range = np.array(None)
+    A = rpsr.pseudoSR(conf, upscale_kernel=kernel[0, 3], kernel_indx=10).WrapArchitecture_PyTorch()
+    taps = torch.load(OUT / "pseudosr_taps.pt", weights_only=True)
+    ds = taps["ds_kernel"].float()
+    hr = synth.synthetic_clip(3, 256, seed=11) * 2 - 1
+    x = (hr + 0.2 * torch.randn(hr.shape, generator=torch.Generator().manual_seed(3))).clamp(-1, 1)
+    y = degrade.blur_down(hr, ds)
+    y_ref = A.DownscaleOP(hr)
+    print("oracle blur_down vs reference DownscaleOP at 256:", float((y - y_ref).abs().max()))
+    R = A.A_pinv(y, x)
+    torch.save({"R": R.clone(), "down_hr": y_ref.clone(), "hr_seed": 11, "noise_seed": 3, "frames": 3, "size": 256},
+               OUT / "dc_gaussian_256.pt")
+    print("wrote dc_gaussian_256.pt", tuple(R.shape), float(R.abs().mean()))
 
 
 def _bicubic_kernel(factor):
@@ -305,5 +329,7 @@ if __name__ == "__main__":
         tattn()
     elif what == "ragged":
         ragged()
+    elif what == "ops256":
+        ops256()
     else:
         raise SystemExit(__doc__)
